@@ -1,0 +1,80 @@
+// common.cuh -- shared helpers for libdne.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdarg.h>
+#include <string.h>
+
+#include "../../include/dne.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "libdne is written for sm_100a (B200) only"
+#endif
+
+struct dne_ctx {
+    int device;
+    int sm_count;
+    const float* noise;     // borrowed
+    int64_t noise_count;
+    double* scratch;        // owned: DNE_SCRATCH_DOUBLES doubles
+};
+#define DNE_SCRATCH_DOUBLES 16384
+
+void dne_set_error(const char* fmt, ...);
+
+#define DNE_CHECK_ARG(cond, msg)                                   \
+    do {                                                           \
+        if (!(cond)) {                                             \
+            dne_set_error("%s: %s", __func__, msg);                \
+            return DNE_ERR_ARG;                                    \
+        }                                                          \
+    } while (0)
+
+#define DNE_CUDA(call)                                                                 \
+    do {                                                                               \
+        cudaError_t e__ = (call);                                                      \
+        if (e__ != cudaSuccess) {                                                      \
+            dne_set_error("%s: %s -> %s", __func__, #call, cudaGetErrorString(e__));   \
+            return DNE_ERR_CUDA;                                                       \
+        }                                                                              \
+    } while (0)
+
+#define DNE_LAUNCH_CHECK()                                                             \
+    do {                                                                               \
+        cudaError_t e__ = cudaGetLastError();                                          \
+        if (e__ != cudaSuccess) {                                                      \
+            dne_set_error("%s: kernel launch -> %s", __func__, cudaGetErrorString(e__)); \
+            return DNE_ERR_CUDA;                                                       \
+        }                                                                              \
+    } while (0)
+
+static inline int64_t cdiv64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// ---- device helpers --------------------------------------------------------------------------------
+__device__ __forceinline__ float4 ldg_stream_f4(const float* p) {
+    // streaming 128-bit load: read-only path, do not allocate in L1 (data is touched once)
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ float ldg_stream_f1(const float* p) {
+    float r;
+    asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(r) : "l"(p));
+    return r;
+}
+
+__device__ __forceinline__ float apply_act(float x, int act) {
+    if (act == DNE_ACT_RELU) return fmaxf(x, 0.0f);
+    if (act == DNE_ACT_TANH) return tanhf(x);
+    return x;
+}
+
+template <typename T>
+__device__ __forceinline__ T warp_sum(T v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}

@@ -1,0 +1,232 @@
+// dne_api.cu -- C ABI of libdne.so: context, error reporting, forward orchestration (include/dne.h).
+#include "common.cuh"
+#include "forward.cuh"
+
+static thread_local char g_err[512] = "";
+
+void dne_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+extern "C" const char* dne_last_error(void) { return g_err; }
+extern "C" int dne_version(void) { return 100; }
+extern "C" int dne_abi_sizes(int* layer_desc_bytes, int* net_desc_bytes) {
+    if (layer_desc_bytes) *layer_desc_bytes = (int)sizeof(dne_layer_desc);
+    if (net_desc_bytes) *net_desc_bytes = (int)sizeof(dne_net_desc);
+    return DNE_OK;
+}
+
+extern "C" int dne_ctx_create(int device, dne_ctx** out) {
+    DNE_CHECK_ARG(out, "out is null");
+    *out = nullptr;
+    int n = 0;
+    DNE_CUDA(cudaGetDeviceCount(&n));
+    DNE_CHECK_ARG(device >= 0 && device < n, "no such CUDA device");
+    DNE_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    DNE_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) {
+        dne_set_error("dne_ctx_create: device %d is sm_%d%d; libdne is built for sm_100a (B200) only", device,
+                      prop.major, prop.minor);
+        return DNE_ERR_CUDA;
+    }
+    dne_ctx* c = new dne_ctx();
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    c->noise = nullptr;
+    c->noise_count = 0;
+    c->scratch = nullptr;
+    cudaError_t e = cudaMalloc(&c->scratch, sizeof(double) * DNE_SCRATCH_DOUBLES);
+    if (e != cudaSuccess) {
+        delete c;
+        dne_set_error("dne_ctx_create: cudaMalloc -> %s", cudaGetErrorString(e));
+        return DNE_ERR_CUDA;
+    }
+    *out = c;
+    return DNE_OK;
+}
+
+extern "C" int dne_ctx_destroy(dne_ctx* ctx) {
+    if (!ctx) return DNE_OK;
+    cudaSetDevice(ctx->device);
+    if (ctx->scratch) cudaFree(ctx->scratch);
+    delete ctx;
+    return DNE_OK;
+}
+
+extern "C" int dne_noise_bind(dne_ctx* ctx, const float* d_noise, int64_t count) {
+    DNE_CHECK_ARG(ctx && d_noise && count > 0, "bad arguments");
+    DNE_CHECK_ARG(((uintptr_t)d_noise & 15) == 0, "noise table must be 16-byte aligned");
+    ctx->noise = d_noise;
+    ctx->noise_count = count;
+    return DNE_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// forward planning: workspace carve-up
+// ---------------------------------------------------------------------------------------------------
+constexpr int PLAN_SM_COUNT = 148;   // B200; planning must not depend on a live device (ws query works on CPU)
+
+struct ForwardPlan {
+    size_t x0_off;                         // normalised vector observations
+    size_t act_off[DNE_MAX_LAYERS];
+    int64_t act_elems[DNE_MAX_LAYERS];     // per slot
+    DensePlan dense[DNE_MAX_LAYERS];
+    size_t part_theta_off, part_noise_off;
+    size_t total;
+};
+
+static int64_t layer_out_elems(const dne_layer_desc& L) {
+    return L.kind == DNE_CONV ? (int64_t)L.hout * L.hout * L.cout : (int64_t)L.cout;
+}
+
+static int plan_forward(const dne_net_desc* net, int n_slots, int paired, bool shared_theta, ForwardPlan* fp) {
+    DNE_CHECK_ARG(net && net->n_layers >= 1 && net->n_layers <= DNE_MAX_LAYERS, "bad net descriptor");
+    size_t off = 0;
+    fp->x0_off = off;
+    if (net->ob_kind == DNE_OB_VECTOR) off += align_up((size_t)n_slots * net->ob_dim * sizeof(float), 256);
+    size_t pt = 0, pn = 0;
+    for (int l = 0; l < net->n_layers; ++l) {
+        const dne_layer_desc& L = net->layers[l];
+        fp->act_elems[l] = layer_out_elems(L);
+        fp->act_off[l] = off;
+        off += align_up((size_t)n_slots * fp->act_elems[l] * sizeof(float), 256);
+        if (L.kind == DNE_DENSE) {
+            const bool head = (l == net->n_layers - 1);
+            fp->dense[l] = dne_plan_dense(L, n_slots, paired, shared_theta && !head, PLAN_SM_COUNT);
+            if (fp->dense[l].part_theta_floats > pt) pt = fp->dense[l].part_theta_floats;
+            if (fp->dense[l].part_noise_floats > pn) pn = fp->dense[l].part_noise_floats;
+        }
+    }
+    fp->part_theta_off = off;
+    off += align_up(pt * sizeof(float), 256);
+    fp->part_noise_off = off;
+    off += align_up(pn * sizeof(float), 256);
+    fp->total = off;
+    return DNE_OK;
+}
+
+extern "C" int dne_forward_ws_bytes(const dne_net_desc* net, int n_slots, size_t* out_bytes) {
+    DNE_CHECK_ARG(out_bytes && n_slots >= 0, "bad arguments");
+    ForwardPlan a, b;
+    int rc = plan_forward(net, n_slots, 0, true, &a);
+    if (rc) return rc;
+    rc = plan_forward(net, n_slots + (n_slots & 1), 1, true, &b);
+    if (rc) return rc;
+    *out_bytes = a.total > b.total ? a.total : b.total;
+    return DNE_OK;
+}
+
+static int forward_impl(dne_ctx* ctx, const dne_net_desc* net, const float* d_theta, const int64_t* d_noise_idx,
+                        const float* d_scale, const int32_t* d_theta_idx, const uint8_t* d_active, int n_slots,
+                        int paired, const void* d_obs, const float* d_ob_mean, const float* d_ob_std,
+                        const float* d_vbn, int32_t* d_actions, float* d_out, void* d_ws, size_t ws_bytes,
+                        void* stream) {
+    DNE_CHECK_ARG(ctx && ctx->noise, "noise table not bound (dne_noise_bind)");
+    DNE_CHECK_ARG(net && d_theta && d_noise_idx && d_scale && d_obs && d_ws, "null pointer");
+    DNE_CHECK_ARG(n_slots >= 0, "n_slots < 0");
+    DNE_CHECK_ARG(!paired || (n_slots % 2 == 0), "paired mode needs an even number of slots");
+    DNE_CHECK_ARG(net->num_params <= ctx->noise_count, "net larger than the noise table");
+    DNE_CHECK_ARG(((uintptr_t)d_ws & 255) == 0, "workspace must be 256-byte aligned");
+    if (n_slots == 0) return DNE_OK;
+    ForwardPlan fp;
+    int rc = plan_forward(net, n_slots, paired, d_theta_idx == nullptr, &fp);
+    if (rc) return rc;
+    if (ws_bytes < fp.total) {
+        dne_set_error("forward: workspace too small (%zu < %zu)", ws_bytes, fp.total);
+        return DNE_ERR_WS;
+    }
+    bool needs_vbn = false;
+    for (int l = 0; l < net->n_layers; ++l) needs_vbn = needs_vbn || (net->layers[l].bn == DNE_BN_TF);
+    DNE_CHECK_ARG(!needs_vbn || d_vbn, "net has batch-norm layers: d_vbn (dne_vbn_reference_pass) required");
+
+    cudaStream_t st = (cudaStream_t)stream;
+    char* ws = (char*)d_ws;
+    SlotArgs sa;
+    sa.theta = d_theta;
+    sa.noise = ctx->noise;
+    sa.noise_idx = d_noise_idx;
+    sa.scale = d_scale;
+    sa.theta_idx = d_theta_idx;
+    sa.active = d_active;
+    sa.P = net->num_params;
+
+    const void* cur = d_obs;
+    int64_t cur_elems = net->ob_dim;
+    bool cur_u8 = (net->ob_kind == DNE_OB_ATARI_U8);
+    if (net->ob_kind == DNE_OB_VECTOR) {
+        float* x0 = (float*)(ws + fp.x0_off);
+        dne_launch_ob_norm((const float*)d_obs, d_ob_mean, d_ob_std, (int64_t)n_slots * net->ob_dim, net->ob_dim,
+                           x0, st);
+        DNE_LAUNCH_CHECK();
+        cur = x0;
+    } else {
+        cur_elems = 84 * 84 * 4;
+    }
+    for (int l = 0; l < net->n_layers; ++l) {
+        const dne_layer_desc& L = net->layers[l];
+        const bool last = (l == net->n_layers - 1);
+        float* out = (float*)(ws + fp.act_off[l]);
+        int64_t out_stride = fp.act_elems[l];
+        if (last && d_out) { out = d_out; out_stride = net->n_out; }
+        LayerEpi epi;
+        epi.off_b = L.off_b;
+        epi.off_beta = L.off_beta;
+        epi.off_gamma = L.off_gamma;
+        epi.act = L.act;
+        epi.bn = L.bn;
+        epi.bn_off = L.bn_off;
+        epi.vbn_len = net->vbn_len;
+        epi.vbn = d_vbn;
+        if (L.kind == DNE_CONV) {
+            DNE_CHECK_ARG((int64_t)L.hin * L.hin * L.cin == cur_elems, "conv layer input size mismatch");
+            rc = dne_launch_conv_layer(sa, L, epi, cur_u8, cur, cur_elems, 0, out, out_stride, 0, n_slots, 1, st);
+            if (rc) {
+                dne_set_error("forward: conv layer %d shape not compiled in (cin %d cout %d k %d s %d hin %d)", l,
+                              L.cin, L.cout, L.ksize, L.stride, L.hin);
+                return rc;
+            }
+        } else {
+            DNE_CHECK_ARG(!cur_u8, "dense layer cannot read uint8 observations");
+            DNE_CHECK_ARG(L.cin == cur_elems, "dense layer input size mismatch");
+            rc = dne_launch_dense_layer(ctx, sa, L, epi, fp.dense[l], (const float*)cur, cur_elems, out, out_stride,
+                                        last ? d_actions : nullptr, (float*)(ws + fp.part_theta_off),
+                                        (float*)(ws + fp.part_noise_off), n_slots, st);
+            if (rc) {
+                dne_set_error("forward: dense layer %d (%d x %d) not supported", l, L.cin, L.cout);
+                return rc;
+            }
+        }
+        DNE_LAUNCH_CHECK();
+        cur = out;
+        cur_elems = fp.act_elems[l];
+        cur_u8 = false;
+    }
+    return DNE_OK;
+}
+
+extern "C" int dne_perturb_forward_conv(dne_ctx* ctx, const dne_net_desc* net, const float* d_theta,
+                                        const int64_t* d_noise_idx, const float* d_scale,
+                                        const int32_t* d_theta_idx, const uint8_t* d_active, int n_slots, int paired,
+                                        const uint8_t* d_obs, const float* d_vbn, int32_t* d_actions,
+                                        float* d_logits, void* d_ws, size_t ws_bytes, void* stream) {
+    DNE_CHECK_ARG(net && net->ob_kind == DNE_OB_ATARI_U8, "net must take uint8 Atari observations");
+    DNE_CHECK_ARG(net->layers[net->n_layers - 1].kind == DNE_DENSE, "last layer must be dense");
+    return forward_impl(ctx, net, d_theta, d_noise_idx, d_scale, d_theta_idx, d_active, n_slots, paired, d_obs,
+                        nullptr, nullptr, d_vbn, d_actions, d_logits, d_ws, ws_bytes, stream);
+}
+
+extern "C" int dne_perturb_forward_mlp(dne_ctx* ctx, const dne_net_desc* net, const float* d_theta,
+                                       const int64_t* d_noise_idx, const float* d_scale, const int32_t* d_theta_idx,
+                                       const uint8_t* d_active, int n_slots, int paired, const float* d_obs,
+                                       const float* d_ob_mean, const float* d_ob_std, float* d_actions_out,
+                                       void* d_ws, size_t ws_bytes, void* stream) {
+    DNE_CHECK_ARG(net && net->ob_kind == DNE_OB_VECTOR, "net must take float vector observations");
+    DNE_CHECK_ARG(d_actions_out, "d_actions_out is null");
+    DNE_CHECK_ARG((d_ob_mean == nullptr) == (d_ob_std == nullptr), "ob_mean / ob_std must both be given or both null");
+    return forward_impl(ctx, net, d_theta, d_noise_idx, d_scale, d_theta_idx, d_active, n_slots, paired, d_obs,
+                        d_ob_mean, d_ob_std, nullptr, nullptr, d_actions_out, d_ws, ws_bytes, stream);
+}

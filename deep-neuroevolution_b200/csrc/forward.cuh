@@ -1,0 +1,41 @@
+// forward.cuh -- declarations shared by forward_kernels.cu / vbn_kernels.cu / dne_api.cu
+#pragma once
+#include "common.cuh"
+
+struct SlotArgs {
+    const float* theta;        // [n_theta, P]
+    const float* noise;        // slab
+    const int64_t* noise_idx;  // [n_slots]
+    const float* scale;        // [n_slots]
+    const int32_t* theta_idx;  // nullable
+    const uint8_t* active;     // nullable
+    int64_t P;
+};
+
+struct LayerEpi {
+    int64_t off_b, off_beta, off_gamma;
+    int act, bn, bn_off, vbn_len;
+    const float* vbn;          // [n_slots, vbn_len]
+};
+
+struct DensePlan {
+    bool decomposed;
+    int n_split, k_per_split;     // theta GEMM split-K
+    int G, rows_per_chunk, n_chunks, rw;
+    size_t part_theta_floats, part_noise_floats;
+};
+
+DensePlan dne_plan_dense(const dne_layer_desc& L, int n_slots, int paired, bool shared_theta, int sm_count);
+
+int dne_launch_conv_layer(const SlotArgs& sa, const dne_layer_desc& L, const LayerEpi& epi, bool in_u8,
+                          const void* in, int64_t in_slot_stride, int64_t in_img_stride, float* out,
+                          int64_t out_slot_stride, int64_t out_img_stride, int n_slots, int n_img,
+                          cudaStream_t st);
+
+int dne_launch_dense_layer(const dne_ctx* ctx, const SlotArgs& sa, const dne_layer_desc& L, const LayerEpi& epi,
+                           const DensePlan& p, const float* X, int64_t x_slot_stride, float* out,
+                           int64_t out_slot_stride, int32_t* actions, float* part_theta, float* part_noise,
+                           int n_slots, cudaStream_t st);
+
+void dne_launch_ob_norm(const float* obs, const float* mean, const float* stdv, int64_t total, int dim, float* out,
+                        cudaStream_t st);

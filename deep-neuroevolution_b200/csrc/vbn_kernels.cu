@@ -1,0 +1,266 @@
+// vbn_kernels.cu -- virtual batch norm reference pass (ESAtariPolicy).
+//
+//   es_distributed/policies.py:322,324,328  layers.batch_norm(scale=True, is_training=is_ref, decay=0., epsilon=1e-3)
+//   es_distributed/policies.py:332-335,399  the 128-observation reference batch is forwarded before every rollout
+//   es_distributed/es.py:105-113,160-162    reference batch = 128 random-action observations, shared by all members
+//
+// Per member: forward the shared reference batch layer by layer with the member's perturbed weights; after each
+// BN'd layer take the batch mean / biased variance per channel (these become the member's "moving" statistics
+// because decay = 0), normalise, activate, continue.  This is the one sub-problem of the path with real weight
+// reuse per member (M = n_ref*441 rows per member for conv1): a dense contraction.
+#include "common.cuh"
+#include "forward.cuh"
+
+__device__ __forceinline__ bool v_slot_active(const SlotArgs& a, int slot) { return !a.active || a.active[slot]; }
+__device__ __forceinline__ const float* v_slot_theta(const SlotArgs& a, int slot) {
+    return a.theta + (a.theta_idx ? (int64_t)a.theta_idx[slot] * a.P : 0);
+}
+__device__ __forceinline__ float v_perturbed(float th, float s, float n) { return __fadd_rn(th, __fmul_rn(s, n)); }
+
+// ---- per-member GEMM: out[slot][m][n] = sum_k X[slot][m][k] * (theta_w + s*noise)[k][n] + bias_n ------------
+constexpr int MG_BM = 128, MG_BN = 64, MG_BK = 16, MG_TM = 8, MG_TN = 4, MG_THREADS = 256;
+
+__global__ void __launch_bounds__(MG_THREADS)
+member_gemm_kernel(SlotArgs sa, int64_t off_w, int64_t off_b, const float* __restrict__ X, int64_t x_slot_stride,
+                   int M, int K, int N, float* __restrict__ out, int64_t out_slot_stride) {
+    const int slot = blockIdx.z;
+    if (!v_slot_active(sa, slot)) return;
+    __shared__ __align__(16) float As[MG_BK][MG_BM];
+    __shared__ __align__(16) float Bs[MG_BK][MG_BN];
+    const int tid = threadIdx.x;
+    const int tx = tid % (MG_BN / MG_TN), ty = tid / (MG_BN / MG_TN);
+    const int m0 = blockIdx.y * MG_BM, n0 = blockIdx.x * MG_BN;
+    const float* th = v_slot_theta(sa, slot);
+    const int64_t idx = sa.noise_idx[slot];
+    const float s = sa.scale[slot];
+    const float* tw = th + off_w;
+    const float* nz = sa.noise + idx + off_w;
+    const float* x = X + (int64_t)slot * x_slot_stride;
+
+    float acc[MG_TM][MG_TN];
+#pragma unroll
+    for (int i = 0; i < MG_TM; ++i)
+#pragma unroll
+        for (int j = 0; j < MG_TN; ++j) acc[i][j] = 0.0f;
+
+    for (int k0 = 0; k0 < K; k0 += MG_BK) {
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {                       // A: 128 x 16 = 512 float4 units
+            const int u = tid + i * MG_THREADS;
+            const int ml = u % MG_BM, kq = u / MG_BM;
+            const int m = m0 + ml, k = k0 + 4 * kq;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (m < M && k < K) v = *reinterpret_cast<const float4*>(x + (int64_t)m * K + k);
+            As[4 * kq + 0][ml] = v.x;
+            As[4 * kq + 1][ml] = v.y;
+            As[4 * kq + 2][ml] = v.z;
+            As[4 * kq + 3][ml] = v.w;
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {                       // B: 16 x 64 member weights
+            const int e = tid + i * MG_THREADS;
+            const int kl = e / MG_BN, nl = e % MG_BN;
+            const int k = k0 + kl, n = n0 + nl;
+            float w = 0.0f;
+            if (k < K && n < N) {
+                const int64_t f = (int64_t)k * N + n;
+                w = v_perturbed(tw[f], s, nz[f]);
+            }
+            Bs[kl][nl] = w;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < MG_BK; ++k) {
+            float a[MG_TM], b[MG_TN];
+            const float4 a0 = *reinterpret_cast<const float4*>(&As[k][ty * MG_TM]);
+            const float4 a1 = *reinterpret_cast<const float4*>(&As[k][ty * MG_TM + 4]);
+            const float4 b0 = *reinterpret_cast<const float4*>(&Bs[k][tx * MG_TN]);
+            a[0] = a0.x; a[1] = a0.y; a[2] = a0.z; a[3] = a0.w; a[4] = a1.x; a[5] = a1.y; a[6] = a1.z; a[7] = a1.w;
+            b[0] = b0.x; b[1] = b0.y; b[2] = b0.z; b[3] = b0.w;
+#pragma unroll
+            for (int i = 0; i < MG_TM; ++i)
+#pragma unroll
+                for (int j = 0; j < MG_TN; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+        }
+        __syncthreads();
+    }
+    float* o = out + (int64_t)slot * out_slot_stride;
+#pragma unroll
+    for (int j = 0; j < MG_TN; ++j) {
+        const int n = n0 + tx * MG_TN + j;
+        if (n >= N) continue;
+        const float bias = (off_b >= 0) ? v_perturbed(th[off_b + n], s, sa.noise[idx + off_b + n]) : 0.0f;
+#pragma unroll
+        for (int i = 0; i < MG_TM; ++i) {
+            const int m = m0 + ty * MG_TM + i;
+            if (m < M) o[(int64_t)m * N + n] = acc[i][j] + bias;
+        }
+    }
+}
+
+// ---- batch statistics: mean and biased variance per (slot, channel) over `rows` rows ---------------------------
+// grid (ceil(C/32), n_slots), 256 threads = 8 row-readers x 32 channels; float64 accumulation, two passes.
+__global__ void __launch_bounds__(256)
+vbn_stats_kernel(SlotArgs sa, const float* __restrict__ Y, int64_t y_slot_stride, int rows, int C,
+                 float* __restrict__ vbn, int vbn_len, int bn_off) {
+    const int slot = blockIdx.y;
+    if (!v_slot_active(sa, slot)) return;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + lane;
+    const float* y = Y + (int64_t)slot * y_slot_stride;
+    __shared__ double sh[8][33];
+    double sum = 0.0;
+    if (c < C)
+        for (int r = w; r < rows; r += 8) sum += (double)y[(int64_t)r * C + c];
+    sh[w][lane] = sum;
+    __syncthreads();
+    double mean = 0.0;
+    for (int i = 0; i < 8; ++i) mean += sh[i][lane];
+    mean /= (double)rows;
+    const float mean_f = (float)mean;
+    __syncthreads();
+    double ss = 0.0;
+    if (c < C)
+        for (int r = w; r < rows; r += 8) {
+            const double d = (double)y[(int64_t)r * C + c] - (double)mean_f;
+            ss += d * d;
+        }
+    sh[w][lane] = ss;
+    __syncthreads();
+    if (w == 0 && c < C) {
+        double v = 0.0;
+        for (int i = 0; i < 8; ++i) v += sh[i][lane];
+        float* st = vbn + (int64_t)slot * vbn_len + bn_off;
+        st[c] = mean_f;
+        st[C + c] = (float)(v / (double)rows);
+    }
+}
+
+// ---- normalise + scale/shift + activation in place --------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+vbn_apply_kernel(SlotArgs sa, float* __restrict__ Y, int64_t y_slot_stride, int64_t elems, int C, int act,
+                 int64_t off_beta, int64_t off_gamma, const float* __restrict__ vbn, int vbn_len, int bn_off) {
+    const int slot = blockIdx.y;
+    if (!v_slot_active(sa, slot)) return;
+    const float* th = v_slot_theta(sa, slot);
+    const int64_t idx = sa.noise_idx[slot];
+    const float s = sa.scale[slot];
+    const float* st = vbn + (int64_t)slot * vbn_len + bn_off;
+    float* y = Y + (int64_t)slot * y_slot_stride;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < elems; e += (int64_t)gridDim.x * blockDim.x) {
+        const int c = (int)(e % C);
+        const float inv = __fdiv_rn(1.0f, __fsqrt_rn(st[C + c] + 1e-3f));
+        const float gamma = v_perturbed(th[off_gamma + c], s, sa.noise[idx + off_gamma + c]);
+        const float beta = v_perturbed(th[off_beta + c], s, sa.noise[idx + off_beta + c]);
+        y[e] = apply_act((y[e] - st[c]) * inv * gamma + beta, act);
+    }
+}
+
+__global__ void act_inplace_kernel(float* __restrict__ y, int64_t total, int act) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < total) y[i] = apply_act(y[i], act);
+}
+
+static int64_t v_layer_out_elems(const dne_layer_desc& L) {
+    return L.kind == DNE_CONV ? (int64_t)L.hout * L.hout * L.cout : (int64_t)L.cout;
+}
+
+static int last_bn_layer(const dne_net_desc* net) {
+    int last = -1;
+    for (int l = 0; l < net->n_layers; ++l)
+        if (net->layers[l].bn == DNE_BN_TF) last = l;
+    return last;
+}
+
+extern "C" int dne_vbn_ws_bytes(const dne_net_desc* net, int n_slots, int n_ref, size_t* out_bytes) {
+    DNE_CHECK_ARG(net && out_bytes && n_slots >= 0 && n_ref >= 1, "bad arguments");
+    const int last = last_bn_layer(net);
+    size_t total = 0;
+    for (int l = 0; l <= last; ++l)
+        total += align_up((size_t)n_slots * n_ref * v_layer_out_elems(net->layers[l]) * sizeof(float), 256);
+    *out_bytes = total;
+    return DNE_OK;
+}
+
+extern "C" int dne_vbn_reference_pass(dne_ctx* ctx, const dne_net_desc* net, const float* d_theta,
+                                      const int64_t* d_noise_idx, const float* d_scale, const int32_t* d_theta_idx,
+                                      const uint8_t* d_active, int n_slots, const uint8_t* d_ref, int n_ref,
+                                      float* d_vbn, void* d_ws, size_t ws_bytes, void* stream) {
+    DNE_CHECK_ARG(ctx && ctx->noise, "noise table not bound (dne_noise_bind)");
+    DNE_CHECK_ARG(net && d_theta && d_noise_idx && d_scale && d_ref && d_vbn && d_ws, "null pointer");
+    DNE_CHECK_ARG(net->ob_kind == DNE_OB_ATARI_U8 && n_ref >= 1 && n_slots >= 0, "bad arguments");
+    if (n_slots == 0) return DNE_OK;
+    const int last = last_bn_layer(net);
+    DNE_CHECK_ARG(last >= 0 && net->vbn_len > 0, "net has no batch-norm layers");
+    size_t need = 0;
+    dne_vbn_ws_bytes(net, n_slots, n_ref, &need);
+    if (ws_bytes < need) {
+        dne_set_error("dne_vbn_reference_pass: workspace too small (%zu < %zu)", ws_bytes, need);
+        return DNE_ERR_WS;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    SlotArgs sa;
+    sa.theta = d_theta;
+    sa.noise = ctx->noise;
+    sa.noise_idx = d_noise_idx;
+    sa.scale = d_scale;
+    sa.theta_idx = d_theta_idx;
+    sa.active = d_active;
+    sa.P = net->num_params;
+
+    char* ws = (char*)d_ws;
+    size_t off = 0;
+    const void* cur = d_ref;
+    int64_t cur_elems = 84 * 84 * 4;      // per image
+    bool cur_u8 = true;
+    for (int l = 0; l <= last; ++l) {
+        const dne_layer_desc& L = net->layers[l];
+        const int64_t oe = v_layer_out_elems(L);
+        float* out = (float*)(ws + off);
+        off += align_up((size_t)n_slots * n_ref * oe * sizeof(float), 256);
+        const int64_t out_slot_stride = (int64_t)n_ref * oe;
+        LayerEpi epi;                      // raw pre-BN output: bias only
+        epi.off_b = L.off_b; epi.off_beta = -1; epi.off_gamma = -1;
+        epi.act = DNE_ACT_NONE; epi.bn = DNE_BN_NONE; epi.bn_off = 0; epi.vbn_len = 0; epi.vbn = nullptr;
+        if (L.kind == DNE_CONV) {
+            DNE_CHECK_ARG((int64_t)L.hin * L.hin * L.cin == cur_elems, "conv layer input size mismatch");
+            // layer 0 reads the SHARED reference batch (slot stride 0); later layers read the member's own buffer
+            const int64_t in_slot_stride = cur_u8 ? 0 : (int64_t)n_ref * cur_elems;
+            int rc = dne_launch_conv_layer(sa, L, epi, cur_u8, cur, in_slot_stride, cur_elems, out, out_slot_stride,
+                                           oe, n_slots, n_ref, st);
+            if (rc) {
+                dne_set_error("dne_vbn_reference_pass: conv layer %d shape not compiled in", l);
+                return rc;
+            }
+        } else {
+            DNE_CHECK_ARG(!cur_u8 && L.cin == cur_elems && L.cin % 4 == 0, "dense layer input mismatch");
+            dim3 grid((L.cout + MG_BN - 1) / MG_BN, (n_ref + MG_BM - 1) / MG_BM, n_slots);
+            member_gemm_kernel<<<grid, MG_THREADS, 0, st>>>(sa, L.off_w, L.off_b, (const float*)cur,
+                                                           (int64_t)n_ref * cur_elems, n_ref, L.cin, L.cout, out,
+                                                           out_slot_stride);
+        }
+        DNE_LAUNCH_CHECK();
+        const int C = L.cout;
+        const int rows = (int)(out_slot_stride / C);
+        if (L.bn == DNE_BN_TF) {
+            vbn_stats_kernel<<<dim3((C + 31) / 32, n_slots), 256, 0, st>>>(sa, out, out_slot_stride, rows, C, d_vbn,
+                                                                          net->vbn_len, L.bn_off);
+            DNE_LAUNCH_CHECK();
+            if (l < last) {
+                const int gx = (int)((out_slot_stride + 255) / 256 < 1024 ? (out_slot_stride + 255) / 256 : 1024);
+                vbn_apply_kernel<<<dim3(gx, n_slots), 256, 0, st>>>(sa, out, out_slot_stride, out_slot_stride, C,
+                                                                   L.act, L.off_beta, L.off_gamma, d_vbn,
+                                                                   net->vbn_len, L.bn_off);
+                DNE_LAUNCH_CHECK();
+            }
+        } else if (L.act != DNE_ACT_NONE && l < last) {
+            const int64_t total = (int64_t)n_slots * out_slot_stride;
+            act_inplace_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(out, total, L.act);
+            DNE_LAUNCH_CHECK();
+        }
+        cur = out;
+        cur_elems = oe;
+        cur_u8 = false;
+    }
+    return DNE_OK;
+}
