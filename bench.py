@@ -1,0 +1,391 @@
+#!/usr/bin/env python
+"""bench.py -- env-steps/sec across the ES population (BASELINE.json metric) on N B200s of one node.
+
+Workload (BASELINE.json configs[1]): Frostbite-shaped ES generation, population 1000
+(n = 500 antithetic pairs), LargeModel conv policy (P = 4,052,658, 18 actions), 256 env slots per GPU, synthetic
+uint8 84x84x4 observations, fixed episode length T (default 1000 env steps), population sharded over the ranks.
+One "step" = one GENERATION: rollouts of this rank's shard of the population for T ticks each, then the update
+(all_gather returns -> centred ranks -> ES gradient over the local noise indices -> all_reduce(g) -> Adam).
+
+  value   device-resident: observations / rewards already in HBM when the timed region starts.
+  e2e     the same generation through the public API es_distributed.es.run_master with a HOST environment: every
+          tick copies that tick's observations host->device from pinned memory and the actions device->host.
+  --impl reference   the reference worker/master loop restated on the CPU (oracle/cpu_worker.py) on all host cores.
+
+Timing: >= 3 warm-up steps; device timing with CUDA events bracketed by barrier + synchronize, max over ranks.
+Every tick streams >= 1 GB of noise slices (>> 126 MB L2) so no input survives in L2 between timed iterations
+(config.l2: "inputs larger than L2").
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "deep-neuroevolution_b200")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import numpy as np   # noqa: E402
+
+NET = "LargeModel"
+POP = 1000
+SLOTS = 256
+SIGMA, L2, LR = 0.005, 0.005, 0.01          # configurations/frostbite_es.json
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--episode-len", type=int, default=int(os.environ.get("DNE_BENCH_T", 1000)))
+    ap.add_argument("--pop", type=int, default=POP)
+    ap.add_argument("--slots", type=int, default=SLOTS)
+    ap.add_argument("--noise-count", type=int, default=int(os.environ.get("DNE_NOISE_COUNT", 250_000_000)))
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-sample-steps", type=int, default=40, help="env steps per episode in the CPU sample")
+    return ap.parse_args()
+
+
+def load_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return json.load(f), "measured"
+    except Exception:
+        return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0}, "fallback"
+
+
+# ---------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        time.sleep(0.05)
+        sm = [float(r[1]) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 8 and r[2].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 8 for i in range(4) if r[4 + i].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def exp_dict(args):
+    """The experiment the e2e leg drives through es_distributed.es.run_master -- configurations/frostbite_es.json
+    with the headline population / policy (BASELINE.json configs[1])."""
+    return {
+        "config": {"calc_obstat_prob": 0.0, "episodes_per_batch": args.pop, "eval_prob": 0.0, "l2coeff": L2,
+                   "noise_stdev": SIGMA, "snapshot_freq": 0, "timesteps_per_batch": 1,
+                   "return_proc_mode": "centered_rank", "episode_cutoff_mode": args.episode_len},
+        "env_id": "FrostbiteNoFrameskip-v4", "synthetic_episode_len": args.episode_len,
+        "optimizer": {"args": {"stepsize": LR}, "type": "adam"},
+        "policy": {"args": {}, "type": "LargeModelPolicy"},
+    }
+
+
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    from dne import _ffi as F, nets, shard
+    from dne.engine import ESUpdate, SlotForward, make_context
+    from dne.noise import SharedNoiseTable
+    import ctypes as C
+
+    rank, world, local = shard.init_from_env("nccl")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}"
+    peaks, peak_src = load_peaks()
+    L = F.lib()
+
+    t0 = time.time()
+    noise = SharedNoiseTable(count=args.noise_count, device=dev)
+    ctx = make_context(local, noise)
+    t_noise = time.time() - t0
+    net = nets.make_net(NET)
+    P = net.num_params
+    T, n_pairs = args.episode_len, args.pop // 2
+    rs = np.random.RandomState(0)
+    theta0 = (rs.randn(P) * 0.05).astype(np.float32)           # random-init weights of the named architecture
+
+    # ------------------------------------------------------------------ value: device-resident generation
+    lo, hi = shard.shard_bounds(n_pairs, rank, world)
+    upd = ESUpdate(ctx, theta0, "adam", stepsize=LR)
+    half = args.slots // 2                                       # two half tables on two streams: the conv phase of
+    sfs = [SlotForward(ctx, net, half) for _ in range(2)]       # one half overlaps the HBM-bound phase of the other
+    streams = [torch.cuda.Stream(device=dev) for _ in range(2)]
+    R = 4                                                        # observation pool blocks, rotated every tick
+    pool = torch.randint(0, 256, (R, args.slots, 84, 84, 4), dtype=torch.uint8, device=dev)
+    rew_pool = (torch.rand(64, args.slots, device=dev) < 0.05).float() * 10.0
+    ret_acc = torch.zeros(args.slots, device=dev)
+    idx_stream = np.random.RandomState(1)
+    tally = {"launches": 0, "pairs": 0}
+
+    def generation_value():
+        idx_all = np.array([noise.sample_index(idx_stream, P) for _ in range(n_pairs)], dtype=np.int64)
+        my = idx_all[lo:hi]
+        returns = torch.zeros(len(my), 2, device=dev)
+        pairs_per_wave = args.slots // 2
+        cur = torch.cuda.current_stream()
+        for w0 in range(0, len(my), pairs_per_wave):
+            wave = my[w0:w0 + pairs_per_wave]
+            npw = len(wave)
+            # split the wave's pairs over the two half tables
+            cut = (npw + 1) // 2
+            parts = [wave[:cut], wave[cut:]]
+            for h in range(2):
+                k = len(parts[h])
+                act = np.zeros(half, dtype=np.uint8)
+                act[:2 * k] = 1
+                ii = np.zeros(half, dtype=np.int64)
+                ii[:2 * k] = np.repeat(parts[h], 2)
+                sc = np.tile([SIGMA, -SIGMA], half // 2).astype(np.float32)
+                sfs[h].set_slots(ii, sc, active=act if 2 * k < half else None)
+            ret_acc.zero_()
+            for s in streams:
+                s.wait_stream(cur)
+            for t in range(T):
+                blk = pool[t % R]
+                for h in range(2):
+                    if len(parts[h]) == 0:
+                        continue
+                    tally["launches"] += 1
+                    tally["pairs"] += len(parts[h])
+                    with torch.cuda.stream(streams[h]):
+                        sfs[h].forward(upd.theta, blk[h * half:(h + 1) * half], paired=True)
+                        ret_acc[h * half:(h + 1) * half] += rew_pool[t % 64, h * half:(h + 1) * half]
+            for s in streams:
+                cur.wait_stream(s)
+            r = torch.cat([ret_acc[:2 * cut], ret_acc[half:half + 2 * (npw - cut)]]).view(-1, 2)
+            returns[w0:w0 + npw] = r
+        allret = shard.all_gather_rows(returns, n_pairs)
+        proc, _ = upd.centered_ranks(allret)
+        g = upd.gradient(proc[lo:hi].contiguous(), torch.from_numpy(my).to(dev), denom=2 * n_pairs)
+        shard.all_reduce_sum_(g)
+        upd.step(L2)
+
+    def timed(fn, steps, warmup, profile=False):
+        for _ in range(warmup):
+            fn()
+        torch.cuda.synchronize()
+        shard.barrier()
+        torch.cuda.synchronize()
+        if profile:
+            F.check(L.dne_profile_enable(ctx.handle, 1, 16384))
+        L.dne_launch_count(1)
+        sampler = ClockSampler(local)
+        if rank == 0:
+            sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        shard.barrier()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        clocks = sampler.stop() if rank == 0 else None
+        launches = L.dne_launch_count(0)
+        prof = None
+        if profile:
+            n, tot = C.c_int(), C.c_double()
+            F.check(L.dne_profile_enable(ctx.handle, 0, 0))
+            F.check(L.dne_profile_read(ctx.handle, C.byref(n), C.byref(tot)))
+            prof = (n.value, tot.value)
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), clocks, launches, prof
+
+    ms_val, clocks, launches, prof = timed(generation_value, args.steps, args.warmup, profile=True)
+    env_steps = args.steps * args.pop * T
+    value = env_steps / (ms_val / 1e3)
+
+    # roofline of the dominant kernel: dense_noise_gemv on the fc layer (97.8% of the weight bytes)
+    fc = net.layers[3]
+    n_timed, tot_ms = prof
+    # algorithmic bytes one launch must read: one noise slice per PAIR (pair-shared) for the fc weights.  The
+    # SURVEY 8d per-env-step figure (4*P + obs + action, every member reading its own slice) is reported beside it.
+    pairs_per_launch = tally["pairs"] / max(tally["launches"], 1)      # average over every forward of the run
+    alg_bytes = pairs_per_launch * 4.0 * fc.cin * fc.cout
+    survey_bytes = 2 * pairs_per_launch * (4.0 * P + 84 * 84 * 4 + 4)
+    avg_ms = tot_ms / max(n_timed, 1)
+    achieved = alg_bytes / (avg_ms * 1e-3) / 1e9 if n_timed else None
+    roofline = {"bound": "hbm", "kernel": "dense_noise_gemv_kernel<2,8> (fc 7744x512 noise GEMV, pair-shared slice)",
+                "achieved": achieved, "peak": peaks["hbm_gbs"], "peak_source": peak_src, "unit": "GB/s",
+                "frac": (achieved / peaks["hbm_gbs"]) if achieved else None,
+                "traffic": None, "launches_timed": n_timed, "avg_launch_ms": avg_ms,
+                "algorithmic_bytes_per_launch": alg_bytes, "pairs_per_launch": pairs_per_launch,
+                "survey_bytes_per_launch": survey_bytes,
+                "frac_survey_bytes": (survey_bytes / (avg_ms * 1e-3) / 1e9 / peaks["hbm_gbs"]) if n_timed else None}
+
+    # ------------------------------------------------------------------ e2e: public API, host environment
+    e2e = None
+    if not args.no_e2e:
+        from es_distributed import es as ES
+        from dne.envs import SyntheticAtariEnv
+        ES.set_default_noise(noise)
+        ES._STATE["ctx"] = ctx
+        env = SyntheticAtariEnv(args.slots, episode_len=T, seed=rank)
+        marks = {}
+
+        io = {"h2d": 0, "d2h": 0}
+
+        def on_it(it, stats, extra):
+            if it > args.warmup:
+                io["h2d"] += extra["forward_launches"] * extra["slots_per_launch"] * 84 * 84 * 4
+                io["d2h"] += extra["forward_launches"] * extra["slots_per_launch"] * 4
+            if it == args.warmup or it == args.warmup + args.steps:
+                torch.cuda.synchronize()
+                shard.barrier()
+                torch.cuda.synchronize()
+                marks[it] = time.perf_counter()
+        ES.run_master(None, None, exp_dict(args), max_iterations=args.warmup + args.steps, n_slots=args.slots,
+                      env=env, noise=noise, seed=0, on_iteration=on_it)
+        dt = marks[args.warmup + args.steps] - marks[args.warmup]
+        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt = float(tt.item())
+        e2e = {"value": env_steps / dt, "unit": "env-steps/s", "ms_per_step": dt * 1e3 / args.steps,
+               "h2d_bytes_per_step": int(io["h2d"] / args.steps), "d2h_bytes_per_step": int(io["d2h"] / args.steps),
+               "bytes_scope": "rank 0's copies per generation (every rank copies the same amount +-1 pair)",
+               "api": "es_distributed.es.run_master(exp) + dne.envs.SyntheticAtariEnv (host, pinned)"}
+
+    # ------------------------------------------------------------------ CPU baseline (rank 0, N == 1 only)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_baseline(args, noise_host=None)
+
+    if rank == 0:
+        line = {
+            "metric": "env-steps/sec across ES population (whole box)", "value": value, "unit": "env-steps/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_val / args.steps,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"frostbite_es_pop{args.pop}_LargeModel_{args.slots}slots_T{T}",
+                       "population": args.pop, "noise_pairs": n_pairs, "policy": "LargeModel (P=4052658, 18 actions)",
+                       "env_slots_per_gpu": args.slots, "episode_len": T, "noise_table": args.noise_count,
+                       "sharding": f"population over {world} rank(s); all_gather(returns)+all_reduce(g)",
+                       "l2": "inputs larger than L2 (>=1 GB of noise slices streamed per tick)",
+                       "step": "one generation (rollouts + update)"},
+            "generation_wall_clock_s": ms_val / args.steps / 1e3,
+            "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
+            "noise_table_build_s": t_noise,
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def cpu_baseline(args, noise_host):
+    """Reference worker loop + master update on the host cores, bounded sample (oracle/cpu_worker.py)."""
+    from oracle import oracle as O
+    from oracle import cpu_worker as W
+    cores = W.host_cores()
+    net = O.make_net(NET)
+    P = net.num_params
+    count = max(P + 1_000_000, min(args.noise_count, 30_000_000))   # bounded table for the sample (same slices' statistics)
+    if noise_host is None:
+        noise_host = O.noise_table(count)
+    rs = np.random.RandomState(0)
+    theta = (rs.randn(P) * 0.05).astype(np.float32)
+    n_pairs = cores                                                  # one pair per worker process
+    idx = rs.randint(0, len(noise_host) - P + 1, size=n_pairs).astype(np.int64)
+    Ts = args.cpu_sample_steps
+    steps, wall, busy = W.measure_workers(NET, noise_host, theta, list(idx), Ts, SIGMA, cores)
+    # master update on a bounded sample of slices, scaled to n = pop/2
+    n_upd = 50
+    uidx = rs.randint(0, len(noise_host) - P + 1, size=n_upd).astype(np.int64)
+    ret = rs.permutation(2 * n_upd).astype(np.float32).reshape(n_upd, 2)
+    upd_s, _ = W.measure_master_update(noise_host, theta, uidx, ret)
+    upd_full = upd_s * (args.pop // 2) / n_upd
+    rollout_rate = steps / wall
+    gen_s = args.pop * args.episode_len / rollout_rate + upd_full
+    return {"value": args.pop * args.episode_len / gen_s, "unit": "env-steps/s", "cores": cores, "kind": "port",
+            "sample": f"{n_pairs} antithetic pairs x {Ts} env steps on {cores} forked 1-thread workers "
+                      f"({steps} steps in {wall:.1f}s) + master update on {n_upd} slices scaled to {args.pop // 2}",
+            "rollout_env_steps_per_s": rollout_rate, "master_update_s_per_generation": upd_full,
+            "generation_wall_clock_s": gen_s}
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path (restated: oracle/cpu_worker.py), all host
+    cores, same metric / config; each step is a bounded sample of the workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import oracle as O
+    from oracle import cpu_worker as W
+    cores = W.host_cores()
+    net = O.make_net(NET)
+    P = net.num_params
+    noise_host = O.noise_table(max(P + 1_000_000, min(args.noise_count, 30_000_000)))
+    rs = np.random.RandomState(0)
+    theta = (rs.randn(P) * 0.05).astype(np.float32)
+    Ts = args.cpu_sample_steps
+    n_upd = 50
+    vals, times = [], []
+    for it in range(args.warmup + args.steps):
+        idx = rs.randint(0, len(noise_host) - P + 1, size=cores).astype(np.int64)
+        steps, wall, _ = W.measure_workers(NET, noise_host, theta, list(idx), Ts, SIGMA, cores, seed=it)
+        uidx = rs.randint(0, len(noise_host) - P + 1, size=n_upd).astype(np.int64)
+        ret = rs.permutation(2 * n_upd).astype(np.float32).reshape(n_upd, 2)
+        upd_s, _ = W.measure_master_update(noise_host, theta, uidx, ret)
+        gen_s = args.pop * args.episode_len / (steps / wall) + upd_s * (args.pop // 2) / n_upd
+        if it >= args.warmup:
+            vals.append(args.pop * args.episode_len / gen_s)
+            times.append(wall + upd_s)
+    v = float(np.mean(vals))
+    sample = (f"per step: {cores} antithetic pairs x {Ts} env steps on {cores} forked 1-thread workers + master update "
+              f"on {n_upd} slices scaled to {args.pop // 2}; generation time extrapolated to pop {args.pop} x T {args.episode_len}")
+    print(json.dumps({
+        "impl": "reference", "metric": "env-steps/sec across ES population (whole box)", "value": v,
+        "unit": "env-steps/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": float(np.mean(times)) * 1e3, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"frostbite_es_pop{args.pop}_LargeModel_{args.slots}slots_T{args.episode_len}",
+                   "population": args.pop, "policy": "LargeModel (P=4052658, 18 actions)", "episode_len": args.episode_len},
+        "cpu_baseline": {"value": v, "unit": "env-steps/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "reference TF/redis workers cannot run (tensorflow, gym, ALE, redis absent): CPU restatement of "
+                "es.py:411-426 + policies.py:399-409 and es.py:273-301 (oracle/cpu_worker.py)"}))
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_b200(a)

@@ -18,7 +18,12 @@ struct dne_ctx {
     const float* noise;     // borrowed
     int64_t noise_count;
     double* scratch;        // owned: DNE_SCRATCH_DOUBLES doubles
+    // optional CUDA-event timing of the dominant kernel (dense_noise_gemv) on the launching stream
+    cudaEvent_t* ev;        // 2 * ev_cap events
+    int ev_cap, ev_n, prof_on;
 };
+extern unsigned long long g_dne_launches;   // kernels launched by this library (process-wide)
+#define DNE_LAUNCHED(n) (g_dne_launches += (unsigned long long)(n))
 #define DNE_SCRATCH_DOUBLES 16384
 
 void dne_set_error(const char* fmt, ...);
@@ -40,6 +45,7 @@ void dne_set_error(const char* fmt, ...);
         }                                                                              \
     } while (0)
 
+#define DNE_LAUNCH_CHECK1() do { DNE_LAUNCHED(1); DNE_LAUNCH_CHECK(); } while (0)
 #define DNE_LAUNCH_CHECK()                                                             \
     do {                                                                               \
         cudaError_t e__ = cudaGetLastError();                                          \

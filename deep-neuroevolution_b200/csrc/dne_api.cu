@@ -3,6 +3,7 @@
 #include "forward.cuh"
 
 static thread_local char g_err[512] = "";
+unsigned long long g_dne_launches = 0;
 
 void dne_set_error(const char* fmt, ...) {
     va_list ap;
@@ -39,6 +40,8 @@ extern "C" int dne_ctx_create(int device, dne_ctx** out) {
     c->noise = nullptr;
     c->noise_count = 0;
     c->scratch = nullptr;
+    c->ev = nullptr;
+    c->ev_cap = c->ev_n = c->prof_on = 0;
     cudaError_t e = cudaMalloc(&c->scratch, sizeof(double) * DNE_SCRATCH_DOUBLES);
     if (e != cudaSuccess) {
         delete c;
@@ -53,7 +56,54 @@ extern "C" int dne_ctx_destroy(dne_ctx* ctx) {
     if (!ctx) return DNE_OK;
     cudaSetDevice(ctx->device);
     if (ctx->scratch) cudaFree(ctx->scratch);
+    if (ctx->ev) {
+        for (int i = 0; i < 2 * ctx->ev_cap; ++i) cudaEventDestroy(ctx->ev[i]);
+        delete[] ctx->ev;
+    }
     delete ctx;
+    return DNE_OK;
+}
+
+// ---- measurement hooks -------------------------------------------------------------------------------
+extern "C" long long dne_launch_count(int reset) {
+    const long long v = (long long)g_dne_launches;
+    if (reset) g_dne_launches = 0;
+    return v;
+}
+
+// Time every dense_noise_gemv launch (the HBM-bound kernel) with CUDA events on the launching stream, up to
+// `capacity` launches.  on = 0 stops recording; the samples stay readable.
+extern "C" int dne_profile_enable(dne_ctx* ctx, int on, int capacity) {
+    DNE_CHECK_ARG(ctx, "ctx is null");
+    if (on) {
+        if (capacity < 1) capacity = 4096;
+        if (capacity > ctx->ev_cap) {
+            if (ctx->ev) {
+                for (int i = 0; i < 2 * ctx->ev_cap; ++i) cudaEventDestroy(ctx->ev[i]);
+                delete[] ctx->ev;
+            }
+            ctx->ev = new cudaEvent_t[2 * (size_t)capacity];
+            for (int i = 0; i < 2 * capacity; ++i) DNE_CUDA(cudaEventCreate(&ctx->ev[i]));
+            ctx->ev_cap = capacity;
+        }
+        ctx->ev_n = 0;
+    }
+    ctx->prof_on = on ? 1 : 0;
+    return DNE_OK;
+}
+
+// Synchronises the device, then returns the number of timed launches and their summed duration (ms).
+extern "C" int dne_profile_read(dne_ctx* ctx, int* n_launches, double* total_ms) {
+    DNE_CHECK_ARG(ctx && n_launches && total_ms, "bad arguments");
+    DNE_CUDA(cudaDeviceSynchronize());
+    double tot = 0.0;
+    for (int i = 0; i < ctx->ev_n; ++i) {
+        float ms = 0.f;
+        DNE_CUDA(cudaEventElapsedTime(&ms, ctx->ev[2 * i], ctx->ev[2 * i + 1]));
+        tot += ms;
+    }
+    *n_launches = ctx->ev_n;
+    *total_ms = tot;
     return DNE_OK;
 }
 

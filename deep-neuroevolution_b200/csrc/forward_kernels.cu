@@ -412,57 +412,57 @@ dense_combine_kernel(SlotArgs sa, LayerEpi epi, int n_slots, int N, int G, const
 // ---------------------------------------------------------------------------------------------------
 constexpr int DS_THREADS = 256, DS_MAXN = 256;
 
+// Thread t < RG*N owns output column n = t % N and row group rg = t / N (RG = 256 / N row groups): one iteration
+// of the k loop covers RG consecutive rows = RG*N CONTIGUOUS weights, so the theta / noise loads are flat and
+// perfectly coalesced whatever N is (18, 17, ...).
 __global__ void __launch_bounds__(DS_THREADS)
 dense_small_kernel(SlotArgs sa, int64_t off_w, LayerEpi epi, const float* __restrict__ X, int64_t x_slot_stride,
                    int K, int N, float* __restrict__ out, int64_t out_slot_stride, int32_t* __restrict__ actions) {
     const int slot = blockIdx.x;
     if (!slot_active(sa, slot)) return;
-    __shared__ float red[DS_THREADS / 32][DS_MAXN];
+    __shared__ float red[DS_THREADS];
     __shared__ float ys[DS_MAXN];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int RG = DS_THREADS / N;
+    const int t = threadIdx.x;
+    const int n = t % N, rg = t / N;
     const float* th = slot_theta(sa, slot);
     const int64_t idx = sa.noise_idx[slot];
     const float s = sa.scale[slot];
     const float* tw = th + off_w;
     const float* nz = sa.noise + idx + off_w;
     const float* x = X + (int64_t)slot * x_slot_stride;
-    constexpr int NJ = DS_MAXN / 32;
-    float acc[NJ];
-#pragma unroll
-    for (int j = 0; j < NJ; ++j) acc[j] = 0.0f;
-    for (int k = warp; k < K; k += DS_THREADS / 32) {
-        const float xk = x[k];
-#pragma unroll
-        for (int j = 0; j < NJ; ++j) {
-            const int n = lane + 32 * j;
-            if (n < N) {
-                const int64_t f = (int64_t)k * N + n;
-                acc[j] = fmaf(xk, perturbed(tw[f], s, nz[f]), acc[j]);
-            }
+    float acc0 = 0.0f, acc1 = 0.0f;
+    if (rg < RG) {
+        int k = rg;
+        for (; k + RG < K; k += 2 * RG) {                      // two independent rows in flight
+            const int64_t f0 = (int64_t)k * N + n, f1 = (int64_t)(k + RG) * N + n;
+            const float t0 = tw[f0], n0 = nz[f0], t1 = tw[f1], n1 = nz[f1];
+            acc0 = fmaf(x[k], perturbed(t0, s, n0), acc0);
+            acc1 = fmaf(x[k + RG], perturbed(t1, s, n1), acc1);
+        }
+        if (k < K) {
+            const int64_t f0 = (int64_t)k * N + n;
+            acc0 = fmaf(x[k], perturbed(tw[f0], s, nz[f0]), acc0);
         }
     }
-#pragma unroll
-    for (int j = 0; j < NJ; ++j) {
-        const int n = lane + 32 * j;
-        if (n < N) red[warp][n] = acc[j];
-    }
+    red[t] = acc0 + acc1;
     __syncthreads();
-    for (int n = threadIdx.x; n < N; n += DS_THREADS) {
+    if (t < N) {
         float sum = 0.0f;
-        for (int w = 0; w < DS_THREADS / 32; ++w) sum += red[w][n];
-        const ChanEpi ce = make_chan_epi(sa, epi, slot, N, n, th, idx, s);
+        for (int g = 0; g < RG; ++g) sum += red[g * N + t];
+        const ChanEpi ce = make_chan_epi(sa, epi, slot, N, t, th, idx, s);
         const float y = ce.apply(sum);
-        ys[n] = y;
-        if (out) out[(int64_t)slot * out_slot_stride + n] = y;
+        ys[t] = y;
+        if (out) out[(int64_t)slot * out_slot_stride + t] = y;
     }
     __syncthreads();
     if (actions && threadIdx.x == 0) {
         int best = 0;
         float bv = ys[0];
-        for (int n = 1; n < N; ++n) {
-            const float v = ys[n];
+        for (int j = 1; j < N; ++j) {
+            const float v = ys[j];
             if (bv != bv) break;                   // a NaN already is the maximum (numpy argmax)
-            if (v > bv || v != v) { bv = v; best = n; }
+            if (v > bv || v != v) { bv = v; best = j; }
         }
         actions[slot] = best;
     }
@@ -492,6 +492,7 @@ static void launch_conv(const SlotArgs& sa, const dne_layer_desc& L, const Layer
     dim3 grid((HOUT * HOUT + BM - 1) / BM, n_slots, n_img);
     conv_kernel<CIN, COUT, KS, STRIDE, HIN, HOUT, PAD, IN_U8, BM, TM, TN><<<grid, THREADS, 0, st>>>(
         sa, L.off_w, epi, in, in_slot_stride, in_img_stride, out, out_slot_stride, out_img_stride);
+    DNE_LAUNCHED(1);
 }
 
 static bool conv_is(const dne_layer_desc& L, int cin, int cout, int ks, int stride, int hin, int hout, int pad) {
@@ -562,6 +563,7 @@ int dne_launch_dense_layer(const dne_ctx* ctx, const SlotArgs& sa, const dne_lay
         if (N > DS_MAXN) return DNE_ERR_UNSUP;
         dense_small_kernel<<<n_slots, DS_THREADS, 0, st>>>(sa, L.off_w, epi, X, x_slot_stride, K, N, out,
                                                           out_slot_stride, actions);
+        DNE_LAUNCHED(1);
         return 0;
     }
     if (x_slot_stride != K || actions) return DNE_ERR_UNSUP;   // heads always go through dense_small_kernel
@@ -574,6 +576,8 @@ int dne_launch_dense_layer(const dne_ctx* ctx, const SlotArgs& sa, const dne_lay
         const int groups = (n_slots + p.G - 1) / p.G;
         dim3 grid(p.n_chunks, groups);
         const int threads = (N / 4) * p.rw;
+        const bool prof = ctx->prof_on && ctx->ev_n < ctx->ev_cap;
+        if (prof) cudaEventRecord(ctx->ev[2 * ctx->ev_n], st);
         size_t sm1 = (size_t)p.G * (p.rows_per_chunk + 1) * sizeof(float);
         size_t sm2 = (size_t)p.rw * p.G * (N + 4) * sizeof(float);
         size_t smem = sm1 > sm2 ? sm1 : sm2;
@@ -583,16 +587,22 @@ int dne_launch_dense_layer(const dne_ctx* ctx, const SlotArgs& sa, const dne_lay
         else
             dense_noise_gemv_kernel<1, 8><<<grid, threads, smem, st>>>(sa, L.off_w, X, x_slot_stride, K, N,
                                                                       p.rows_per_chunk, part_noise);
+        if (prof) {
+            cudaEventRecord(ctx->ev[2 * ctx->ev_n + 1], st);
+            const_cast<dne_ctx*>(ctx)->ev_n++;
+        }
     }
     {
         dim3 grid((N + 255) / 256, n_slots);
         dense_combine_kernel<<<grid, 256, 0, st>>>(sa, epi, n_slots, N, p.G, part_theta, p.n_split, part_noise,
                                                   p.n_chunks, out, out_slot_stride);
     }
+    DNE_LAUNCHED(3);
     return 0;
 }
 
 void dne_launch_ob_norm(const float* obs, const float* mean, const float* stdv, int64_t total, int dim, float* out,
                         cudaStream_t st) {
     ob_norm_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(obs, mean, stdv, total, dim, out);
+    DNE_LAUNCHED(1);
 }

@@ -77,12 +77,12 @@ extern "C" int dne_ga_materialize(dne_ctx* ctx, const dne_net_desc* net, const i
             ga_init_normc_kernel<<<(L.cout + 127) / 128, 128, 0, st>>>(nz + L.off_w, rows, L.cout, (float)stdv,
                                                                       d_theta_out + L.off_w);
         }
-        DNE_LAUNCH_CHECK();
+        DNE_LAUNCH_CHECK1();
     }
     if (len > 1) {
         ga_chain_kernel<<<(unsigned)cdiv64(net->num_params, 256), 256, 0, st>>>(ctx->noise, d_seeds, d_powers, len,
                                                                                net->num_params, d_theta_out);
-        DNE_LAUNCH_CHECK();
+        DNE_LAUNCH_CHECK1();
     }
     return DNE_OK;
 }
@@ -93,7 +93,7 @@ extern "C" int dne_ga_mutate(dne_ctx* ctx, const float* d_parent, int64_t seed, 
     DNE_CHECK_ARG(seed >= 0 && seed + P <= ctx->noise_count, "seed out of range");
     ga_mutate_kernel<<<(unsigned)cdiv64(P, 256), 256, 0, (cudaStream_t)stream>>>(d_parent, ctx->noise + seed, power,
                                                                                 P, d_theta_out);
-    DNE_LAUNCH_CHECK();
+    DNE_LAUNCH_CHECK1();
     return DNE_OK;
 }
 
@@ -125,7 +125,7 @@ __global__ void __launch_bounds__(256) ga_truncate_kernel(const float* __restric
 extern "C" int dne_ga_truncate(const float* d_fitness, int pop, int T, int32_t* d_selected, void* stream) {
     DNE_CHECK_ARG(d_fitness && d_selected && pop >= 1 && T >= 1 && T <= pop, "bad arguments");
     ga_truncate_kernel<<<(pop + 255) / 256, 256, 0, (cudaStream_t)stream>>>(d_fitness, pop, T, d_selected);
-    DNE_LAUNCH_CHECK();
+    DNE_LAUNCH_CHECK1();
     return DNE_OK;
 }
 
@@ -223,9 +223,9 @@ extern "C" int dne_knn_novelty(const uint8_t* d_bc, const int32_t* d_bc_len, int
     cudaStream_t st = (cudaStream_t)stream;
     double* dist = (double*)d_ws;
     knn_dist_kernel<<<dim3(A, q), KNN_THREADS, 0, st>>>(d_bc, d_bc_len, d_archive, d_archive_len, t_max, D, dist, A);
-    DNE_LAUNCH_CHECK();
+    DNE_LAUNCH_CHECK1();
     knn_select_kernel<<<q, KNN_THREADS, 0, st>>>(dist, A, k, d_novelty);
-    DNE_LAUNCH_CHECK();
+    DNE_LAUNCH_CHECK1();
     return DNE_OK;
 }
 
@@ -256,6 +256,6 @@ extern "C" int dne_preprocess_atari(const uint8_t* d_prev, const uint8_t* d_cur,
     const int64_t total = (int64_t)n_slots * 84 * 84;
     preprocess_kernel<<<(unsigned)cdiv64(total, 256), 256, 0, (cudaStream_t)stream>>>(
         d_prev, d_cur, reinterpret_cast<uchar4*>(d_stack), d_reset_mask, n_slots, mode);
-    DNE_LAUNCH_CHECK();
+    DNE_LAUNCH_CHECK1();
     return DNE_OK;
 }

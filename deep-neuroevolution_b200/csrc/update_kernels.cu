@@ -52,7 +52,7 @@ extern "C" int dne_centered_rank(const float* d_returns, int count, float* d_cen
     if (count == 0) return DNE_OK;
     centered_rank_kernel<<<(count + 255) / 256, 256, 0, (cudaStream_t)stream>>>(d_returns, count, d_centered,
                                                                                d_ranks);
-    DNE_LAUNCH_CHECK();
+    DNE_LAUNCH_CHECK1();
     return DNE_OK;
 }
 
@@ -140,7 +140,7 @@ extern "C" int dne_es_grad(dne_ctx* ctx, const float* d_proc_n2, const int64_t* 
         es_grad_kernel<1, 8><<<(unsigned)ctas1, GRAD_THREADS, 0, st>>>(ctx->noise, d_proc_n2, d_noise_idx, n, P,
                                                                       inv, d_g, accumulate);
     }
-    DNE_LAUNCH_CHECK();
+    DNE_LAUNCH_CHECK1();
     return DNE_OK;
 }
 
@@ -205,12 +205,20 @@ sgd_kernel(float* __restrict__ theta, float* __restrict__ v, const float* __rest
     block_reduce2_store(s_step, s_theta, partial + 2 * blockIdx.x);
 }
 
-__global__ void ratio_finalize_kernel(const double* __restrict__ partial, int nblocks, float* __restrict__ ratio) {
-    if (threadIdx.x == 0 && blockIdx.x == 0) {
-        double a = 0.0, b = 0.0;
-        for (int i = 0; i < nblocks; ++i) { a += partial[2 * i]; b += partial[2 * i + 1]; }
-        *ratio = (float)(sqrt(a) / sqrt(b));   // optimizers.py:14
+// one block; thread t sums partials t, t+256, ... then a fixed-order tree: deterministic for a given grid
+__global__ void __launch_bounds__(OPT_THREADS)
+ratio_finalize_kernel(const double* __restrict__ partial, int nblocks, float* __restrict__ ratio) {
+    __shared__ double sa[OPT_THREADS], sb[OPT_THREADS];
+    double a = 0.0, b = 0.0;
+    for (int i = threadIdx.x; i < nblocks; i += OPT_THREADS) { a += partial[2 * i]; b += partial[2 * i + 1]; }
+    sa[threadIdx.x] = a;
+    sb[threadIdx.x] = b;
+    __syncthreads();
+    for (int o = OPT_THREADS / 2; o > 0; o >>= 1) {
+        if (threadIdx.x < o) { sa[threadIdx.x] += sa[threadIdx.x + o]; sb[threadIdx.x] += sb[threadIdx.x + o]; }
+        __syncthreads();
     }
+    if (threadIdx.x == 0) *ratio = (float)(sqrt(sa[0]) / sqrt(sb[0]));   // optimizers.py:14
 }
 
 static int opt_grid(const dne_ctx* ctx, int64_t P) {
@@ -231,10 +239,10 @@ extern "C" int dne_adam_step(dne_ctx* ctx, float* d_theta, float* d_m, float* d_
     adam_kernel<<<grid, OPT_THREADS, 0, st>>>(d_theta, d_m, d_v, d_g, P, (float)l2coeff, -(float)a, (float)beta1,
                                              (float)(1.0 - beta1), (float)beta2, (float)(1.0 - beta2),
                                              (float)epsilon, ctx->scratch);
-    DNE_LAUNCH_CHECK();
+    DNE_LAUNCH_CHECK1();
     if (d_update_ratio) {
-        ratio_finalize_kernel<<<1, 32, 0, st>>>(ctx->scratch, grid, d_update_ratio);
-        DNE_LAUNCH_CHECK();
+        ratio_finalize_kernel<<<1, OPT_THREADS, 0, st>>>(ctx->scratch, grid, d_update_ratio);
+        DNE_LAUNCH_CHECK1();
     }
     return DNE_OK;
 }
@@ -246,10 +254,10 @@ extern "C" int dne_sgd_step(dne_ctx* ctx, float* d_theta, float* d_v, const floa
     const int grid = opt_grid(ctx, P);
     sgd_kernel<<<grid, OPT_THREADS, 0, st>>>(d_theta, d_v, d_g, P, (float)l2coeff, (float)momentum,
                                             (float)(1.0 - momentum), (float)(-stepsize), ctx->scratch);
-    DNE_LAUNCH_CHECK();
+    DNE_LAUNCH_CHECK1();
     if (d_update_ratio) {
-        ratio_finalize_kernel<<<1, 32, 0, st>>>(ctx->scratch, grid, d_update_ratio);
-        DNE_LAUNCH_CHECK();
+        ratio_finalize_kernel<<<1, OPT_THREADS, 0, st>>>(ctx->scratch, grid, d_update_ratio);
+        DNE_LAUNCH_CHECK1();
     }
     return DNE_OK;
 }

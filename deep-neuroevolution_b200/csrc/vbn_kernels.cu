@@ -238,6 +238,7 @@ extern "C" int dne_vbn_reference_pass(dne_ctx* ctx, const dne_net_desc* net, con
             member_gemm_kernel<<<grid, MG_THREADS, 0, st>>>(sa, L.off_w, L.off_b, (const float*)cur,
                                                            (int64_t)n_ref * cur_elems, n_ref, L.cin, L.cout, out,
                                                            out_slot_stride);
+            DNE_LAUNCHED(1);
         }
         DNE_LAUNCH_CHECK();
         const int C = L.cout;
@@ -245,18 +246,18 @@ extern "C" int dne_vbn_reference_pass(dne_ctx* ctx, const dne_net_desc* net, con
         if (L.bn == DNE_BN_TF) {
             vbn_stats_kernel<<<dim3((C + 31) / 32, n_slots), 256, 0, st>>>(sa, out, out_slot_stride, rows, C, d_vbn,
                                                                           net->vbn_len, L.bn_off);
-            DNE_LAUNCH_CHECK();
+            DNE_LAUNCH_CHECK1();
             if (l < last) {
                 const int gx = (int)((out_slot_stride + 255) / 256 < 1024 ? (out_slot_stride + 255) / 256 : 1024);
                 vbn_apply_kernel<<<dim3(gx, n_slots), 256, 0, st>>>(sa, out, out_slot_stride, out_slot_stride, C,
                                                                    L.act, L.off_beta, L.off_gamma, d_vbn,
                                                                    net->vbn_len, L.bn_off);
-                DNE_LAUNCH_CHECK();
+                DNE_LAUNCH_CHECK1();
             }
         } else if (L.act != DNE_ACT_NONE && l < last) {
             const int64_t total = (int64_t)n_slots * out_slot_stride;
             act_inplace_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(out, total, L.act);
-            DNE_LAUNCH_CHECK();
+            DNE_LAUNCH_CHECK1();
         }
         cur = out;
         cur_elems = oe;

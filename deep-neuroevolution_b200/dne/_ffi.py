@@ -61,12 +61,14 @@ _SIGS = {
     "dne_sgd_step": [_P, _P, _P, _P, C.c_int64, C.c_double, C.c_double, C.c_double, _P, _P],
     "dne_ga_materialize": [_P, C.POINTER(NetDesc), _P, _P, C.c_int, C.POINTER(C.c_double), C.c_int, _P, _P],
     "dne_abi_sizes": [C.POINTER(C.c_int), C.POINTER(C.c_int)],
+    "dne_profile_enable": [_P, C.c_int, C.c_int],
+    "dne_profile_read": [_P, C.POINTER(C.c_int), C.POINTER(C.c_double)],
     "dne_ga_mutate": [_P, _P, C.c_int64, C.c_float, C.c_int64, _P, _P],
     "dne_ga_truncate": [_P, C.c_int, C.c_int, _P, _P],
     "dne_knn_ws_bytes": [C.c_int, C.c_int, C.POINTER(C.c_size_t)],
     "dne_knn_novelty": [_P, _P, C.c_int, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, C.c_size_t, _P],
 }
-EXPORTS = sorted(list(_SIGS) + ["dne_last_error", "dne_version"])
+EXPORTS = sorted(list(_SIGS) + ["dne_last_error", "dne_version", "dne_launch_count"])
 
 
 def lib():
@@ -85,6 +87,8 @@ def lib():
         L.dne_last_error.argtypes = []
         L.dne_version.restype = C.c_int
         L.dne_version.argtypes = []
+        L.dne_launch_count.restype = C.c_longlong
+        L.dne_launch_count.argtypes = [C.c_int]
         a, b = C.c_int(), C.c_int()
         L.dne_abi_sizes(C.byref(a), C.byref(b))
         if (a.value, b.value) != (C.sizeof(LayerDesc), C.sizeof(NetDesc)):

@@ -135,8 +135,9 @@ class ESUpdate:
         returns_n2.size so per-rank partial gradients simply add up."""
         n = int(noise_idx.numel())
         assert proc_n2.shape == (n, 2)
-        F.check(F.lib().dne_es_grad(self.ctx.handle, F.ptr(proc_n2.contiguous(), torch.float32),
-                                    F.ptr(noise_idx.contiguous(), torch.int64), n, self.P, float(denom),
+        proc_n2, noise_idx = proc_n2.contiguous(), noise_idx.contiguous()   # keep references: F.ptr() borrows
+        F.check(F.lib().dne_es_grad(self.ctx.handle, F.ptr(proc_n2, torch.float32),
+                                    F.ptr(noise_idx, torch.int64), n, self.P, float(denom),
                                     F.ptr(self.g), int(accumulate), F.stream_ptr()))
         return self.g
 

@@ -1,0 +1,330 @@
+"""``es_distributed.es`` -- the reference's ES driver API (es.py:12-23,26-85,125-138,141-353,366-439) on the B200 engine.
+
+Same names, argument meaning and configuration keys: ``Config``, ``Task``, ``Result``, ``RunningStat``,
+``SharedNoiseTable``, ``compute_ranks``, ``compute_centered_ranks``, ``setup``, ``run_master``, ``run_worker``.
+What changed underneath:
+  * no redis: "workers" are the GPU ranks of one torchrun job (or the single process); the master loop and the
+    worker loop of the reference run in the same process, one generation = rollouts of this rank's shard of the
+    perturbations on its env slots, then all_gather(returns) + all_reduce(partial gradient) over NCCL;
+  * theta, Adam state and the noise table never leave HBM; members' weights are never materialised.
+``master_redis_cfg`` / ``relay_redis_cfg`` are accepted and ignored.  ``max_iterations`` (new, optional) bounds
+the otherwise infinite ``while True`` of es.py:193.
+"""
+from __future__ import annotations
+
+import logging
+import time
+from collections import namedtuple
+
+import numpy as np
+import torch
+
+from dne import _ffi as F
+from dne import shard
+from dne.engine import ESUpdate, make_context
+from dne.envs import BatchEnv, make_env
+from dne.noise import SharedNoiseTable
+from dne.rollout import RolloutRunner, Unit
+
+logger = logging.getLogger(__name__)
+
+Config = namedtuple('Config', [
+    'l2coeff', 'noise_stdev', 'episodes_per_batch', 'timesteps_per_batch',
+    'calc_obstat_prob', 'eval_prob', 'snapshot_freq',
+    'return_proc_mode', 'episode_cutoff_mode'
+])
+Task = namedtuple('Task', ['params', 'ob_mean', 'ob_std', 'ref_batch', 'timestep_limit'])
+Result = namedtuple('Result', [
+    'worker_id',
+    'noise_inds_n', 'returns_n2', 'signreturns_n2', 'lengths_n2',
+    'eval_return', 'eval_length',
+    'ob_sum', 'ob_sumsq', 'ob_count'
+])
+
+# ---- process-wide engine state (one GPU per process) -----------------------------------------------------------
+_STATE = {"noise": None, "ctx": None}
+
+
+def default_noise(count=None) -> SharedNoiseTable:
+    if _STATE["noise"] is None:
+        _STATE["noise"] = SharedNoiseTable() if count is None else SharedNoiseTable(count=count)
+    return _STATE["noise"]
+
+
+def set_default_noise(noise: SharedNoiseTable):
+    _STATE["noise"] = noise
+    _STATE["ctx"] = None
+
+
+def default_context() -> F.Context:
+    if _STATE["ctx"] is None:
+        _STATE["ctx"] = make_context(torch.cuda.current_device(), default_noise())
+    return _STATE["ctx"]
+
+
+class RunningStat(object):
+    """es.py:26-48 (host numpy: a few hundred floats per generation, not on the device path)."""
+
+    def __init__(self, shape, eps):
+        self.sum = np.zeros(shape, dtype=np.float32)
+        self.sumsq = np.full(shape, eps, dtype=np.float32)
+        self.count = eps
+
+    def increment(self, s, ssq, c):
+        self.sum += s
+        self.sumsq += ssq
+        self.count += c
+
+    @property
+    def mean(self):
+        return self.sum / self.count
+
+    @property
+    def std(self):
+        return np.sqrt(np.maximum(self.sumsq / self.count - np.square(self.mean), 1e-2))
+
+    def set_from_init(self, init_mean, init_std, init_count):
+        self.sum[:] = init_mean * init_count
+        self.sumsq[:] = (np.square(init_mean) + np.square(init_std)) * init_count
+        self.count = init_count
+
+
+def _device_ranks(x: np.ndarray):
+    import ctypes as C
+    dev = torch.device("cuda", torch.cuda.current_device())
+    t = torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32).ravel()).to(dev)
+    cen = torch.empty_like(t)
+    ranks = torch.empty(t.numel(), dtype=torch.int32, device=dev)
+    F.check(F.lib().dne_centered_rank(F.ptr(t), t.numel(), F.ptr(cen), F.ptr(ranks), F.stream_ptr()))
+    return cen, ranks
+
+
+def compute_ranks(x):
+    """es.py:70-78 (stable tie rule), computed by dne_centered_rank."""
+    assert x.ndim == 1
+    return _device_ranks(x)[1].cpu().numpy().astype(np.int64)
+
+
+def compute_centered_ranks(x):
+    """es.py:81-85."""
+    return _device_ranks(x)[0].cpu().numpy().reshape(x.shape)
+
+
+def itergroups(items, group_size):
+    assert group_size >= 1
+    group = []
+    for x in items:
+        group.append(x)
+        if len(group) == group_size:
+            yield tuple(group)
+            del group[:]
+    if group:
+        yield tuple(group)
+
+
+def get_ref_batch(env: BatchEnv, batch_size=32, rs=None):
+    """es.py:105-113: ``batch_size`` observations collected under random actions (slot 0 of the batched env)."""
+    rs = rs or np.random.RandomState(0)
+    ref_batch = []
+    slot = np.array([0])
+    env.reset(slot)
+    while len(ref_batch) < batch_size:
+        _, done = env.step(slot, env.random_actions(1, rs))
+        if hasattr(env, "advance"):
+            env.advance()
+        ref_batch.append(np.array(env.obs_block(0, 1)[0]))
+        if done[0]:
+            env.reset(slot)
+    return ref_batch
+
+
+def setup(exp, single_threaded, n_slots=256, env=None, seed=None):
+    """es.py:125-138: (config, env, sess, policy).  ``sess`` is None (no TensorFlow); ``env`` is a batched env."""
+    from . import policies
+    config = Config(**exp['config'])
+    if env is None:
+        env = make_env(exp['env_id'], n_slots, seed=0 if seed is None else seed,
+                       episode_len=exp.get('synthetic_episode_len'))
+    policy = getattr(policies, exp['policy']['type'])(env.observation_space, env.action_space, **exp['policy']['args'],
+                                                     seed=seed)
+    return config, env, None, policy
+
+
+def _cutoff(config):
+    """es.py:169-186."""
+    m = config.episode_cutoff_mode
+    if isinstance(m, int):
+        return m, None, None, m, False
+    if m.startswith('adaptive:'):
+        _, args = m.split(':')
+        a0, a1, a2, a3 = args.split(',')
+        return int(a0), float(a1), float(a2), float(a3), True
+    if m == 'env_default':
+        return None, None, None, None, False
+    raise NotImplementedError(m)
+
+
+def _process_returns(config, upd: ESUpdate, returns_n2, signreturns_n2):
+    """es.py:281-288 on the device."""
+    mode = config.return_proc_mode
+    if mode == 'centered_rank':
+        return upd.centered_ranks(returns_n2)[0]
+    if mode == 'sign':
+        return signreturns_n2.to(upd.device, torch.float32)
+    if mode == 'centered_sign_rank':
+        return upd.centered_ranks(signreturns_n2)[0]
+    raise NotImplementedError(mode)
+
+
+class GenerationStats(dict):
+    pass
+
+
+def run_master(master_redis_cfg, log_dir, exp, *, max_iterations=None, n_slots=256, env=None, noise=None, seed=None,
+               on_iteration=None):
+    """es.py:141-353.  Every rank of the job calls this (rank 0 logs); returns the final flat theta (numpy) once
+    ``max_iterations`` generations are done."""
+    from .optimizers import SGD, Adam
+    from . import tabular_logger as tlogger
+    rank, world = shard.dist_info()
+    if rank == 0:
+        logger.info('run_master: {}'.format({'log_dir': log_dir, 'exp': exp}))
+        tlogger.start(log_dir)
+    else:
+        tlogger.set_quiet(True)
+    if noise is not None:
+        set_default_noise(noise)
+    noise = default_noise()
+    ctx = default_context()
+    seed = shard.broadcast_seed(seed)
+    config, env, _, policy = setup(exp, single_threaded=False, n_slots=n_slots, env=env, seed=seed)
+    theta = policy.get_trainable_flat()
+    optimizer = {'sgd': SGD, 'adam': Adam}[exp['optimizer']['type']](theta, ctx=ctx, **exp['optimizer']['args'])
+    policy.bind_theta(optimizer.device_theta)
+    upd: ESUpdate = optimizer._upd
+    rs = np.random.RandomState(seed)          # identical on every rank: same noise-index stream (bit-exact bookkeeping)
+    P = policy.num_params
+
+    ob_stat = None
+    if policy.needs_ob_stat:
+        ob_stat = RunningStat(env.observation_space.shape, eps=1e-2)           # es.py:155-158
+    ref_batch = None
+    if policy.needs_ref_batch:
+        ref_batch = get_ref_batch(env, batch_size=128, rs=np.random.RandomState(seed))   # es.py:160-162
+        policy.set_ref_batch(ref_batch)
+
+    tslimit, incr_tslimit_threshold, tslimit_incr_ratio, tslimit_max, adaptive_tslimit = _cutoff(config)
+    group = 2
+    runner = RolloutRunner(ctx, policy.net, env, n_slots=n_slots, group=group,
+                           pipeline=2 if n_slots % 4 == 0 else 1, ref_batch=policy.ref_batch)
+
+    episodes_so_far = timesteps_so_far = 0
+    tstart = time.time()
+    it = 0
+    while max_iterations is None or it < max_iterations:
+        step_tstart = time.time()
+        it += 1
+        if rank == 0:
+            tlogger.log('********** Iteration {} **********'.format(it))
+        ob_mean = ob_std = None
+        if policy.needs_ob_stat:
+            policy.set_ob_stat(ob_stat.mean, ob_stat.std)                       # es.py:382-383 (task.ob_mean/std)
+            ob_mean, ob_std = policy.ob_mean, policy.ob_std
+
+        noise_inds, returns, signreturns, lengths = [], [], [], []
+        eval_rets, eval_lens = [], []
+        num_eps = num_ts = 0
+        ticks_this_iter = 0
+        first = True
+        # es.py:230: collect until BOTH quotas are met.  First batch = ceil(episodes_per_batch/2) pairs; if the
+        # timestep quota is still short, keep adding world*n_slots/2 pairs at a time.
+        while first or num_eps < config.episodes_per_batch or num_ts < config.timesteps_per_batch:
+            n_pairs = -(-config.episodes_per_batch // 2) if first else world * n_slots // 2
+            n_eval = int(rs.binomial(n_pairs, config.eval_prob)) if (first and config.eval_prob > 0) else 0
+            idx = np.array([noise.sample_index(rs, P) for _ in range(n_pairs)], dtype=np.int64)      # es.py:412
+            sig = np.float32(config.noise_stdev)
+            units = [Unit(int(i), (sig, -sig)) for i in idx] + [Unit(0, (0.0, 0.0)) for _ in range(-(-n_eval // 2))]
+            lo, hi = shard.shard_bounds(len(units), rank, world)
+            res = runner.run(optimizer.device_theta, units[lo:hi], tslimit, ob_mean=ob_mean, ob_std=ob_std,
+                             ac_noise_std=getattr(policy, "ac_noise_std", 0.0), random_stream=rs if world == 1 else
+                             np.random.RandomState(seed + 1000 * it + rank))
+            ticks_this_iter += res.ticks
+            dev = upd.device
+            pack = torch.from_numpy(np.concatenate([res.returns, res.signreturns, res.lengths.astype(np.float32)],
+                                                   axis=1)).to(dev)
+            allr = shard.all_gather_rows(pack, len(units)).cpu().numpy()
+            r_all, s_all, l_all = allr[:, 0:2], allr[:, 2:4], allr[:, 4:6].astype(np.int32)
+            noise_inds.append(idx)
+            returns.append(r_all[:n_pairs]); signreturns.append(s_all[:n_pairs]); lengths.append(l_all[:n_pairs])
+            if n_eval:
+                eval_rets += list(r_all[n_pairs:].ravel()[:n_eval])
+                eval_lens += list(l_all[n_pairs:].ravel()[:n_eval])
+            num_eps += 2 * n_pairs
+            num_ts += int(l_all[:n_pairs].sum())
+            first = False
+
+        noise_inds_n = np.concatenate(noise_inds)
+        returns_n2 = np.concatenate(returns).astype(np.float32)
+        signreturns_n2 = np.concatenate(signreturns).astype(np.float32)
+        lengths_n2 = np.concatenate(lengths)
+        episodes_so_far += lengths_n2.size + len(eval_lens)
+        timesteps_so_far += int(lengths_n2.sum()) + int(np.sum(eval_lens))
+        assert noise_inds_n.shape[0] == returns_n2.shape[0] == lengths_n2.shape[0]
+
+        # ---- update (es.py:281-301) on the device ----
+        dev = upd.device
+        proc = _process_returns(config, upd, torch.from_numpy(returns_n2).to(dev), torch.from_numpy(signreturns_n2).to(dev))
+        n = len(noise_inds_n)
+        lo, hi = shard.shard_bounds(n, rank, world)
+        d_idx = torch.from_numpy(noise_inds_n[lo:hi]).to(dev)
+        g = upd.gradient(proc[lo:hi].contiguous(), d_idx, denom=returns_n2.size)      # partial over this rank's indices
+        shard.all_reduce_sum_(g)                                                      # 4*P bytes over NVLink
+        update_ratio, _ = optimizer.update_from_gradient(g, config.l2coeff)           # es.py:298
+
+        if adaptive_tslimit and (lengths_n2 == tslimit).mean() >= incr_tslimit_threshold:   # es.py:308-311
+            old = tslimit
+            tslimit = min(int(tslimit_incr_ratio * tslimit), tslimit_max)
+            logger.info('Increased timestep limit from {} to {}'.format(old, tslimit))
+
+        step_tend = time.time()
+        stats = GenerationStats(
+            EpRewMean=float(returns_n2.mean()), EpRewStd=float(returns_n2.std()), EpLenMean=float(lengths_n2.mean()),
+            EvalEpRewMean=np.nan if not eval_rets else float(np.mean(eval_rets)),
+            EvalEpRewMedian=np.nan if not eval_rets else float(np.median(eval_rets)),
+            EvalEpRewStd=np.nan if not eval_rets else float(np.std(eval_rets)),
+            EvalEpLenMean=np.nan if not eval_rets else float(np.mean(eval_lens)),
+            EvalPopRank=np.nan if not eval_rets else float(
+                np.searchsorted(np.sort(returns_n2.ravel()), eval_rets).mean() / returns_n2.size),
+            EvalEpCount=len(eval_rets),
+            Norm=float(torch.square(optimizer.device_theta).sum()), GradNorm=float(torch.square(g).sum()),
+            UpdateRatio=float(update_ratio),
+            EpisodesThisIter=int(lengths_n2.size), EpisodesSoFar=int(episodes_so_far),
+            TimestepsThisIter=int(lengths_n2.sum()), TimestepsSoFar=int(timesteps_so_far),
+            UniqueWorkers=world, UniqueWorkersFrac=1.0, ResultsSkippedFrac=0.0, ObCount=0,
+            TimeElapsedThisIter=step_tend - step_tstart, TimeElapsed=step_tend - tstart)
+        if rank == 0:
+            for k, v in stats.items():
+                tlogger.record_tabular(k, v)
+            tlogger.dump_tabular()
+        if on_iteration is not None:
+            on_iteration(it, stats, dict(noise_inds_n=noise_inds_n, returns_n2=returns_n2, lengths_n2=lengths_n2,
+                                         signreturns_n2=signreturns_n2, g=g, theta=optimizer.device_theta,
+                                         forward_launches=ticks_this_iter,
+                                         slots_per_launch=n_slots // len(runner.halves)))
+        if rank == 0 and log_dir and config.snapshot_freq != 0 and it % config.snapshot_freq == 0:   # es.py:345-353
+            import os.path as osp
+            filename = osp.join(log_dir, 'snapshot_iter{:05d}_rew{}.h5'.format(
+                it, np.nan if not eval_rets else int(np.mean(eval_rets))))
+            policy.save(filename)
+            tlogger.log('Saved snapshot {}'.format(filename))
+    return optimizer.theta
+
+
+def run_worker(master_redis_cfg, relay_redis_cfg, noise, *, min_task_runtime=.2, exp=None, **kw):
+    """es.py:366-439.  In this engine a "worker" is a non-zero rank of the torchrun job: it runs the same loop as
+    the master on its shard of the population (NCCL replaces the redis relay)."""
+    assert isinstance(noise, SharedNoiseTable)
+    if exp is None:
+        raise RuntimeError("run_worker needs the experiment dict (there is no redis to fetch it from); "
+                           "launch every rank through `python -m es_distributed.main master` under torchrun")
+    return run_master(master_redis_cfg, None, exp, noise=noise, **kw)

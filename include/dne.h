@@ -86,6 +86,14 @@ int         dne_version(void);
 /* ABI self-check for FFI bindings: sizeof(dne_layer_desc), sizeof(dne_net_desc). */
 int         dne_abi_sizes(int* layer_desc_bytes, int* net_desc_bytes);
 
+/* ---- measurement hooks (bench.py) -------------------------------------------------------------------
+ * dne_launch_count: kernels launched by this library in this process so far (reset != 0 zeroes it).
+ * dne_profile_enable/read: CUDA-event timing of every launch of the dominant HBM-bound kernel
+ * (dense_noise_gemv) on the stream it is launched on; read() synchronises the device. */
+long long   dne_launch_count(int reset);
+int         dne_profile_enable(dne_ctx* ctx, int on, int capacity);
+int         dne_profile_read(dne_ctx* ctx, int* n_launches, double* total_ms);
+
 /* Replaces SharedNoiseTable (es_distributed/es.py:51-67): the table lives in HBM; `count` floats, the
  * allocation must extend at least 8 floats past `count` (aligned vector loads of unaligned slices). */
 int dne_noise_bind(dne_ctx* ctx, const float* d_noise, int64_t count);

@@ -1,0 +1,199 @@
+"""CPU-only tests: the C-ABI library loads and exports every symbol include/dne.h declares (no compute calls
+without a GPU), the host-side network layouts agree with the oracle's independent restatement, the synthetic
+environments, the sharding / collective host logic under gloo at world_size 2, and the CPU baseline worker."""
+import ctypes as C
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _header_symbols():
+    txt = open(os.path.join(ROOT, "include", "dne.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(dne_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_library_exports_every_declared_symbol():
+    from dne import _ffi as F
+    lib = F.lib()                                   # dlopen + struct-size ABI check
+    syms = _header_symbols()
+    assert len(syms) >= 20
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in include/dne.h but not exported by libdne.so"
+    assert set(F.EXPORTS) <= set(syms)
+    assert lib.dne_version() >= 100
+    a, b = C.c_int(), C.c_int()
+    lib.dne_abi_sizes(C.byref(a), C.byref(b))
+    assert (a.value, b.value) == (C.sizeof(F.LayerDesc), C.sizeof(F.NetDesc))
+
+
+def test_no_cpu_fallback():
+    import torch
+    from dne import _ffi as F
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    h = C.c_void_p()
+    assert F.lib().dne_ctx_create(0, C.byref(h)) == -2           # DNE_ERR_CUDA, reported not fatal
+    assert b"dne_ctx_create" in F.lib().dne_last_error()
+    with pytest.raises(F.DneError):
+        F.Context(0)
+    with pytest.raises(F.DneError):
+        F.ptr(torch.zeros(3))
+
+
+def test_ws_queries_run_without_gpu():
+    from dne import _ffi as F, nets
+    for name, slots in (("LargeModel", 256), ("ESAtariPolicy", 256), ("MujocoPolicy", 10000)):
+        net = nets.make_net(name)
+        nb = C.c_size_t()
+        assert F.lib().dne_forward_ws_bytes(C.byref(net.desc), slots, C.byref(nb)) == 0
+        assert 0 < nb.value < 4 << 30
+
+
+@pytest.mark.parametrize("name", ["LargeModel", "Model", "GAAtariPolicy", "ESAtariPolicy", "MujocoPolicy"])
+def test_layouts_match_oracle(name):
+    from dne import _ffi as F, nets
+    net, ref = nets.make_net(name), O.make_net(name)
+    assert net.num_params == ref.num_params
+    for l, lo in zip(net.layers, ref.layers):
+        offs = {v.kind: v.offset for v in lo.vars}
+        assert l.off_w == offs["w"] and l.off_b == offs.get("b", -1)
+        assert l.off_beta == offs.get("beta", -1) and l.off_gamma == offs.get("gamma", -1)
+        if lo.kind == "conv":
+            assert (l.hout, l.pad) == (lo.hout, lo.pad_before)
+    d = net.desc
+    assert d.num_params == net.num_params and d.n_layers == len(net.layers)
+    assert d.vbn_len == sum(2 * l.cout for l in net.layers if l.bn == F.BN_TF)
+
+
+def test_synthetic_envs():
+    from dne.envs import SyntheticAtariEnv, SyntheticVectorEnv
+    env = SyntheticAtariEnv(8, episode_len=5, seed=1, pin=False)
+    assert env.obs_block(0, 8).shape == (8, 84, 84, 4) and env.obs_block(0, 8).dtype.__str__() == "torch.uint8"
+    env.reset(np.arange(8))
+    done_at = None
+    for t in range(5):
+        rew, done = env.step(np.arange(8), np.zeros(8, dtype=np.int32))
+        assert set(np.unique(rew)) <= {0.0, 10.0}
+        env.advance()
+        if done.all():
+            done_at = t
+    assert done_at == 4
+    env2 = SyntheticAtariEnv(4, episode_len=(3, 9), seed=2, pin=False)
+    env2.reset(np.arange(4))
+    assert ((env2.ep_len >= 3) & (env2.ep_len <= 9)).all()
+    v = SyntheticVectorEnv(4, episode_len=3, pin=False)
+    v.reset(np.arange(4))
+    r, d = v.step(np.arange(4), np.zeros((4, 17), np.float32))
+    assert r.shape == (4,) and not d.any()
+
+
+def test_shard_bounds_cover_everything():
+    from dne.shard import shard_bounds
+    for n in (0, 1, 7, 500, 501):
+        for world in (1, 2, 3, 8):
+            got = [shard_bounds(n, r, world) for r in range(world)]
+            assert got[0][0] == 0 and got[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(got, got[1:]))
+            assert max(h - l for l, h in got) - min(h - l for l, h in got) <= 1
+
+
+_GLOO_WORKER = r'''
+import os, sys, numpy as np, torch, torch.distributed as dist
+sys.path[:0] = [%(root)r, os.path.join(%(root)r, "deep-neuroevolution_b200")]
+from dne import shard
+from oracle import oracle as O
+rank, world, _ = shard.init_from_env("gloo")
+assert world == 2
+# one "generation": every rank draws the same index stream, evaluates its shard (fake returns = f(index)),
+# gathers, ranks, forms its partial gradient with the GLOBAL denominator, all-reduces.
+seed = shard.broadcast_seed(None if rank == 0 else 12345)
+rs = np.random.RandomState(seed)
+noise = O.noise_table(50_000)
+P, n = 257, 21
+idx = rs.randint(0, len(noise) - P + 1, size=n).astype(np.int64)
+lo, hi = shard.shard_bounds(n, rank, world)
+local = torch.from_numpy(np.stack([np.sin(idx[lo:hi] * 0.001), np.cos(idx[lo:hi] * 0.002)], axis=1).astype(np.float32))
+allr = shard.all_gather_rows(local, n).numpy()
+expect = np.stack([np.sin(idx * 0.001), np.cos(idx * 0.002)], axis=1).astype(np.float32)
+assert np.array_equal(allr, expect), "gather order"
+proc = O.compute_centered_ranks(allr)
+part = np.zeros(P, dtype=np.float64)
+for i in range(lo, hi):
+    part += np.float64(np.float32(proc[i, 0] - proc[i, 1])) * noise[idx[i]:idx[i] + P].astype(np.float64)
+g = torch.from_numpy((part / allr.size).astype(np.float32))
+shard.all_reduce_sum_(g)
+ref = O.es_gradient(proc, noise, idx, P, dtype=np.float64)
+assert np.abs(g.numpy() - ref).max() <= 1e-5 * np.abs(ref).max()
+shard.barrier()
+if rank == 0:
+    print("GLOO_OK", seed)
+dist.destroy_process_group()
+'''
+
+
+def test_sharded_generation_bookkeeping_gloo_world2(tmp_path):
+    script = tmp_path / "w.py"
+    script.write_text(_GLOO_WORKER % {"root": ROOT})
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29571", str(script)],
+                       capture_output=True, text=True, timeout=240, env=env)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "GLOO_OK" in r.stdout
+
+
+def test_cpu_worker_forward_matches_oracle():
+    from oracle import cpu_worker as W
+    rs = np.random.RandomState(0)
+    for name in ("LargeModel", "ESAtariPolicy"):
+        net = O.make_net(name)
+        theta = (rs.randn(net.num_params) * 0.05).astype(np.float32)
+        for v in net.variables():
+            if v.kind == "gamma":
+                theta[v.offset:v.offset + v.size] = 1.0
+        obs = rs.randint(0, 256, size=(3, 84, 84, 4)).astype(np.uint8)
+        prep = W.prepare(net, theta)
+        stats = None
+        kw = {}
+        if name == "ESAtariPolicy":
+            ref = rs.randint(0, 256, size=(8, 84, 84, 4)).astype(np.uint8)
+            _, stats = W.forward_prepared(net, prep, ref, is_ref=True)
+            _, ostats = O.forward(net, theta, ref, is_ref=True)
+            kw = dict(vbn_stats=ostats)
+            for (m, v), (mo, vo) in zip(stats, ostats):
+                np.testing.assert_allclose(m.numpy(), mo, rtol=1e-4, atol=1e-5)
+                np.testing.assert_allclose(v.numpy(), vo, rtol=1e-3, atol=1e-6)
+        got, _ = W.forward_prepared(net, prep, obs, vbn_stats=stats)
+        want, _ = O.forward(net, theta, obs, **kw)
+        np.testing.assert_allclose(got.numpy(), want, rtol=1e-3, atol=1e-4)
+
+
+def test_cpu_worker_sample_runs():
+    from oracle import cpu_worker as W
+    net = O.make_net("Model")
+    noise = O.noise_table(net.num_params + 10_000)
+    theta = noise[:net.num_params].copy() * np.float32(0.05)
+    steps, wall, busy = W.measure_workers("Model", noise, theta, [3, 77], 4, 0.005, 2)
+    assert steps == 2 * 2 * 4 and wall > 0
+    secs, g = W.measure_master_update(noise, theta, np.array([1, 5, 9]), np.arange(6, dtype=np.float32).reshape(3, 2))
+    assert g.shape == (net.num_params,) and g.dtype == np.float32
+
+
+def test_tabular_logger(tmp_path):
+    from es_distributed import tabular_logger as tl
+    tl.start(str(tmp_path))
+    tl.record_tabular("EpRewMean", 1.5)
+    tl.record_tabular("TimestepsSoFar", 10)
+    tl.dump_tabular()
+    tl.stop()
+    txt = (tmp_path / "log.txt").read_text()
+    assert "EpRewMean" in txt and "TimestepsSoFar" in txt
