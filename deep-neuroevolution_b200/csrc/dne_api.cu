@@ -146,7 +146,7 @@ static int plan_forward(const dne_net_desc* net, int n_slots, int paired, bool s
         off += align_up((size_t)n_slots * fp->act_elems[l] * sizeof(float), 256);
         if (L.kind == DNE_DENSE) {
             const bool head = (l == net->n_layers - 1);
-            fp->dense[l] = dne_plan_dense(L, n_slots, paired, shared_theta && !head, PLAN_SM_COUNT);
+            fp->dense[l] = dne_plan_dense(L, n_slots, head ? -1 : paired, shared_theta, PLAN_SM_COUNT);
             if (fp->dense[l].part_theta_floats > pt) pt = fp->dense[l].part_theta_floats;
             if (fp->dense[l].part_noise_floats > pn) pn = fp->dense[l].part_noise_floats;
         }
@@ -161,12 +161,15 @@ static int plan_forward(const dne_net_desc* net, int n_slots, int paired, bool s
 
 extern "C" int dne_forward_ws_bytes(const dne_net_desc* net, int n_slots, size_t* out_bytes) {
     DNE_CHECK_ARG(out_bytes && n_slots >= 0, "bad arguments");
-    ForwardPlan a, b;
-    int rc = plan_forward(net, n_slots, 0, true, &a);
-    if (rc) return rc;
-    rc = plan_forward(net, n_slots + (n_slots & 1), 1, true, &b);
-    if (rc) return rc;
-    *out_bytes = a.total > b.total ? a.total : b.total;
+    size_t best = 0;
+    for (int shared = 0; shared < 2; ++shared)
+        for (int paired = 0; paired < 3; ++paired) {
+            ForwardPlan a;
+            int rc = plan_forward(net, n_slots + (n_slots & 1), paired, shared != 0, &a);
+            if (rc) return rc;
+            if (a.total > best) best = a.total;
+        }
+    *out_bytes = best;
     return DNE_OK;
 }
 
@@ -178,7 +181,9 @@ static int forward_impl(dne_ctx* ctx, const dne_net_desc* net, const float* d_th
     DNE_CHECK_ARG(ctx && ctx->noise, "noise table not bound (dne_noise_bind)");
     DNE_CHECK_ARG(net && d_theta && d_noise_idx && d_scale && d_obs && d_ws, "null pointer");
     DNE_CHECK_ARG(n_slots >= 0, "n_slots < 0");
-    DNE_CHECK_ARG(!paired || (n_slots % 2 == 0), "paired mode needs an even number of slots");
+    DNE_CHECK_ARG(paired >= 0 && paired <= 2, "paired must be 0, 1 (pairs share the noise index) or 2 (pairs share the theta row)");
+    DNE_CHECK_ARG(!paired || (n_slots % 2 == 0), "paired modes need an even number of slots");
+    DNE_CHECK_ARG(paired != 2 || d_theta_idx, "paired == 2 needs d_theta_idx");
     DNE_CHECK_ARG(net->num_params <= ctx->noise_count, "net larger than the noise table");
     DNE_CHECK_ARG(((uintptr_t)d_ws & 255) == 0, "workspace must be 256-byte aligned");
     if (n_slots == 0) return DNE_OK;

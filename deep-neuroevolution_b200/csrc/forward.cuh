@@ -21,7 +21,7 @@ struct LayerEpi {
 struct DensePlan {
     bool decomposed;
     int n_split, k_per_split;     // theta GEMM split-K
-    int G, rows_per_chunk, n_chunks, rw;
+    int G, Gt, rows_per_chunk, n_chunks, rw;     // Gt: theta group size (0 = shared theta GEMM)
     size_t part_theta_floats, part_noise_floats;
 };
 

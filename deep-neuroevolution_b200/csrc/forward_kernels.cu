@@ -271,9 +271,18 @@ dense_theta_gemm_kernel(const float* __restrict__ X, int M, int K, int N, const 
 // columns.  blockDim = (N/4) * RW: RW row-interleaved readers per column quad, reduced through shared memory.
 // Grid = (chunks of the K rows, groups).  Partials are written per chunk (deterministic, no atomics).
 // ---------------------------------------------------------------------------------------------------
+// The same kernel also streams the PARENT weights for GA slots (theta rows selected per slot): the "slab" is then
+// the theta matrix and the per-group element offset is theta_idx * P (GemvSrc).
+struct GemvSrc {
+    const float* base;        // noise slab, or theta matrix
+    const int64_t* idx64;     // per-slot element offset (noise index) ...
+    const int32_t* idx32;     // ... or per-slot row (theta_idx) times `mul`
+    int64_t mul, off;         // off = layer weight offset inside the flat vector
+};
+
 template <int G, int U>
 __global__ void __launch_bounds__(256)
-dense_noise_gemv_kernel(SlotArgs sa, int64_t off_w, const float* __restrict__ X, int64_t x_slot_stride, int K,
+dense_noise_gemv_kernel(SlotArgs sa, GemvSrc src, const float* __restrict__ X, int64_t x_slot_stride, int K,
                         int N, int rows_per_chunk, float* __restrict__ part) {
     extern __shared__ float smem[];
     const int group = blockIdx.y, chunk = blockIdx.x, n_chunks = gridDim.x;
@@ -300,9 +309,9 @@ dense_noise_gemv_kernel(SlotArgs sa, int64_t off_w, const float* __restrict__ X,
     }
     __syncthreads();
 
-    const int64_t E0 = sa.noise_idx[slot0] + off_w;
+    const int64_t E0 = (src.idx64 ? src.idx64[slot0] : (src.idx32 ? (int64_t)src.idx32[slot0] * src.mul : 0)) + src.off;
     const int a = (int)(E0 & 3);
-    const float* S = sa.noise + (E0 - a) + 4 * t;       // aligned column quad of this thread
+    const float* S = src.base + (E0 - a) + 4 * t;       // aligned column quad of this thread
 
     float acc[G][4];
 #pragma unroll
@@ -387,15 +396,21 @@ dense_noise_gemv_kernel(SlotArgs sa, int64_t off_w, const float* __restrict__ X,
 }
 
 // combine:  y[m][n] = act(bn( sum_split Ytheta + s_m * sum_chunk Ynoise + bias ))
+// theta partials are [split][slot][N] (shared-theta GEMM, Gt == 0) or [group][chunk][Gt][N] (per-parent GEMV).
 __global__ void __launch_bounds__(256)
 dense_combine_kernel(SlotArgs sa, LayerEpi epi, int n_slots, int N, int G, const float* __restrict__ part_theta,
-                     int n_split, const float* __restrict__ part_noise, int n_chunks, float* __restrict__ out,
-                     int64_t out_slot_stride) {
+                     int n_split, int Gt, const float* __restrict__ part_noise, int n_chunks,
+                     float* __restrict__ out, int64_t out_slot_stride) {
     const int slot = blockIdx.y;
     const int n = blockIdx.x * blockDim.x + threadIdx.x;
     if (n >= N || !slot_active(sa, slot)) return;
     float yt = 0.0f;
-    for (int sp = 0; sp < n_split; ++sp) yt += part_theta[((int64_t)sp * n_slots + slot) * N + n];
+    if (Gt == 0) {
+        for (int sp = 0; sp < n_split; ++sp) yt += part_theta[((int64_t)sp * n_slots + slot) * N + n];
+    } else {
+        const float* pt = part_theta + (((int64_t)(slot / Gt) * n_split) * Gt + (slot % Gt)) * N + n;
+        for (int c = 0; c < n_split; ++c) yt += pt[(int64_t)c * Gt * N];
+    }
     const int group = slot / G, g = slot % G;
     float yn = 0.0f;
     const float* pn = part_noise + (((int64_t)group * n_chunks) * G + g) * N + n;
@@ -530,9 +545,12 @@ DensePlan dne_plan_dense(const dne_layer_desc& L, int n_slots, int paired, bool 
     DensePlan p;
     memset(&p, 0, sizeof(p));
     const int K = L.cin, N = L.cout;
-    p.decomposed = shared_theta && (N % 4 == 0) && (K % 4 == 0) && ((int64_t)K * N >= 16384) && (N / 4 <= 256);
+    // paired < 0 marks the output head (needs the argmax epilogue of dense_small_kernel)
+    p.decomposed = (paired >= 0) && (N % 4 == 0) && (K % 4 == 0) && ((int64_t)K * N >= 16384) && (N / 4 <= 256);
     if (!p.decomposed) return p;
-    p.G = paired ? 2 : 1;
+    // paired bit 0: slots (2p,2p+1) share the noise index; bit 1: they share the theta row (GA parent)
+    p.G = (paired & 1) ? 2 : 1;
+    p.Gt = shared_theta ? 0 : ((paired & 2) ? 2 : 1);
     // split-K so that the GEMM grid reaches ~2 waves
     const int tiles = ((n_slots + DG_BM - 1) / DG_BM) * ((N + DG_BN - 1) / DG_BN);
     const int k_tiles = (K + DG_BK - 1) / DG_BK;
@@ -549,6 +567,10 @@ DensePlan dne_plan_dense(const dne_layer_desc& L, int n_slots, int paired, bool 
     while (nq * p.rw * 2 <= 256 && p.rw * 2 <= 8) p.rw *= 2;
     while (nq * p.rw < 64 && p.rw < 8) p.rw *= 2;
     p.part_theta_floats = (size_t)p.n_split * n_slots * N;
+    if (p.Gt) {                                        // per-parent theta streamed by the GEMV kernel
+        p.n_split = p.n_chunks;
+        p.part_theta_floats = (size_t)((n_slots + p.Gt - 1) / p.Gt) * p.n_chunks * p.Gt * N;
+    }
     const int groups = (n_slots + p.G - 1) / p.G;
     p.part_noise_floats = (size_t)groups * p.n_chunks * p.G * N;
     return p;
@@ -567,26 +589,38 @@ int dne_launch_dense_layer(const dne_ctx* ctx, const SlotArgs& sa, const dne_lay
         return 0;
     }
     if (x_slot_stride != K || actions) return DNE_ERR_UNSUP;   // heads always go through dense_small_kernel
-    {
+    const int threads = (N / 4) * p.rw;
+    auto gemv_smem = [&](int G) {
+        size_t sm1 = (size_t)G * (p.rows_per_chunk + 1) * sizeof(float);
+        size_t sm2 = (size_t)p.rw * G * (N + 4) * sizeof(float);
+        return sm1 > sm2 ? sm1 : sm2;
+    };
+    if (p.Gt == 0) {
         dim3 grid((N + DG_BN - 1) / DG_BN, (n_slots + DG_BM - 1) / DG_BM, p.n_split);
         dense_theta_gemm_kernel<<<grid, DG_THREADS, 0, st>>>(X, n_slots, K, N, sa.theta + L.off_w, p.k_per_split,
                                                             part_theta);
+    } else {
+        GemvSrc ts{sa.theta, nullptr, sa.theta_idx, sa.P, L.off_w};
+        dim3 grid(p.n_chunks, (n_slots + p.Gt - 1) / p.Gt);
+        if (p.Gt == 2)
+            dense_noise_gemv_kernel<2, 8><<<grid, threads, gemv_smem(2), st>>>(sa, ts, X, x_slot_stride, K, N,
+                                                                              p.rows_per_chunk, part_theta);
+        else
+            dense_noise_gemv_kernel<1, 8><<<grid, threads, gemv_smem(1), st>>>(sa, ts, X, x_slot_stride, K, N,
+                                                                              p.rows_per_chunk, part_theta);
     }
     {
+        GemvSrc ns{sa.noise, sa.noise_idx, nullptr, 0, L.off_w};
         const int groups = (n_slots + p.G - 1) / p.G;
         dim3 grid(p.n_chunks, groups);
-        const int threads = (N / 4) * p.rw;
         const bool prof = ctx->prof_on && ctx->ev_n < ctx->ev_cap;
         if (prof) cudaEventRecord(ctx->ev[2 * ctx->ev_n], st);
-        size_t sm1 = (size_t)p.G * (p.rows_per_chunk + 1) * sizeof(float);
-        size_t sm2 = (size_t)p.rw * p.G * (N + 4) * sizeof(float);
-        size_t smem = sm1 > sm2 ? sm1 : sm2;
         if (p.G == 2)
-            dense_noise_gemv_kernel<2, 8><<<grid, threads, smem, st>>>(sa, L.off_w, X, x_slot_stride, K, N,
-                                                                      p.rows_per_chunk, part_noise);
+            dense_noise_gemv_kernel<2, 8><<<grid, threads, gemv_smem(2), st>>>(sa, ns, X, x_slot_stride, K, N,
+                                                                              p.rows_per_chunk, part_noise);
         else
-            dense_noise_gemv_kernel<1, 8><<<grid, threads, smem, st>>>(sa, L.off_w, X, x_slot_stride, K, N,
-                                                                      p.rows_per_chunk, part_noise);
+            dense_noise_gemv_kernel<1, 8><<<grid, threads, gemv_smem(1), st>>>(sa, ns, X, x_slot_stride, K, N,
+                                                                              p.rows_per_chunk, part_noise);
         if (prof) {
             cudaEventRecord(ctx->ev[2 * ctx->ev_n + 1], st);
             const_cast<dne_ctx*>(ctx)->ev_n++;
@@ -594,7 +628,7 @@ int dne_launch_dense_layer(const dne_ctx* ctx, const SlotArgs& sa, const dne_lay
     }
     {
         dim3 grid((N + 255) / 256, n_slots);
-        dense_combine_kernel<<<grid, 256, 0, st>>>(sa, epi, n_slots, N, p.G, part_theta, p.n_split, part_noise,
+        dense_combine_kernel<<<grid, 256, 0, st>>>(sa, epi, n_slots, N, p.G, part_theta, p.n_split, p.Gt, part_noise,
                                                   p.n_chunks, out, out_slot_stride);
     }
     DNE_LAUNCHED(3);

@@ -98,7 +98,10 @@ class RolloutRunner:
         self.use_theta_idx = theta.dim() == 2 and theta.shape[0] > 1
         pending = deque(range(n_units))
         remaining = [G] * n_units
-        bc_trace = {}
+        if collect_bc == "trace":                          # per-slot RAM trace buffers, filled with vectorised writes
+            for h in self.halves:
+                if getattr(h, "bc_buf", None) is None or h.bc_buf.shape[1] < limit:
+                    h.bc_buf = np.zeros((h.hi - h.lo, limit, 128), dtype=np.uint8)
         cur = torch.cuda.current_stream()
         for h in self.halves:
             h.unit[:] = -1
@@ -123,8 +126,6 @@ class RolloutRunner:
                     h.active[s], h.fresh[s] = 1, 1
                     h.ret[s] = h.sret[s] = 0.0
                     h.length[s] = 0
-                    if collect_bc == "trace":
-                        bc_trace[(uid, g)] = []
                 env.reset(h.lo + np.arange(u0, u0 + G))
                 h.dirty = True
 
@@ -158,9 +159,7 @@ class RolloutRunner:
             h.length[loc] += 1
             res.steps += len(loc)
             if collect_bc == "trace":
-                ram = env.get_ram(h.lo + loc)
-                for j, s in enumerate(loc):
-                    bc_trace[(h.unit[s], h.member[s])].append(ram[j])
+                h.bc_buf[loc, h.length[loc] - 1] = env.get_ram(h.lo + loc)        # policies.py:410,418
             fin = loc[np.logical_or(done, h.length[loc] >= limit)]
             if len(fin):
                 for s in fin:
@@ -169,7 +168,7 @@ class RolloutRunner:
                     res.signreturns[uid, g] = np.float32(h.sret[s])
                     res.lengths[uid, g] = h.length[s]
                     if collect_bc == "trace":
-                        res.bcs[uid][g] = np.asarray(bc_trace.pop((uid, g)), dtype=np.uint8)
+                        res.bcs[uid][g] = h.bc_buf[s, :h.length[s]].copy()
                     elif collect_bc == "final":
                         res.bcs[uid][g] = env.get_ram(np.array([h.lo + s]))[0]
                     h.active[s] = 0

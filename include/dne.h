@@ -107,7 +107,8 @@ int dne_forward_ws_bytes(const dne_net_desc* net, int n_slots, size_t* out_bytes
  *   policy.act(ob)  -> conv/dense forward + argmax                              (policies.py:319-330,403,449-459;
  *                                                                                models/dqn.py:25-47; indexedmatmul.cpp:148-213)
  * Slot s evaluates weights theta + d_scale[s]*noise[d_noise_idx[s] : +P] (never materialised in HBM).
- * paired != 0 asserts slots (2p, 2p+1) share d_noise_idx (antithetic pair): the slice is then read once.
+ * paired == 1 asserts slots (2p, 2p+1) share d_noise_idx (antithetic pair): the slice is then read once.
+ * paired == 2 asserts slots (2p, 2p+1) share d_theta_idx (GA siblings of one parent): the parent row is read once.
  * d_theta_idx (nullable): per-slot row into d_theta [n_theta, P] (GA parents); NULL = row 0 for every slot.
  * d_active (nullable): uint8 per slot; inactive slots are skipped and their outputs left untouched.
  * d_vbn: per-slot virtual-batch-norm statistics from dne_vbn_reference_pass (NULL if the net has none).
