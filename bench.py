@@ -141,9 +141,13 @@ def run_b200(args):
     # ------------------------------------------------------------------ value: device-resident generation
     lo, hi = shard.shard_bounds(n_pairs, rank, world)
     upd = ESUpdate(ctx, theta0, "adam", stepsize=LR)
-    half = args.slots // 2                                       # two half tables on two streams: the conv phase of
-    sfs = [SlotForward(ctx, net, half) for _ in range(2)]       # one half overlaps the HBM-bound phase of the other
-    streams = [torch.cuda.Stream(device=dev) for _ in range(2)]
+    # One slot table on one stream by default.  DNE_BENCH_STREAMS=2 splits the table over two streams (measured:
+    # +5% only -- the HBM-bound GEMV already fills every SM, so the halves time-slice instead of overlapping -- and it
+    # makes per-kernel event timings overlap, so the roofline leg keeps the single-stream schedule).
+    NS = int(os.environ.get("DNE_BENCH_STREAMS", "1"))
+    part = args.slots // NS
+    sfs = [SlotForward(ctx, net, part) for _ in range(NS)]
+    streams = [torch.cuda.Stream(device=dev) for _ in range(NS)]
     R = 4                                                        # observation pool blocks, rotated every tick
     pool = torch.randint(0, 256, (R, args.slots, 84, 84, 4), dtype=torch.uint8, device=dev)
     rew_pool = (torch.rand(64, args.slots, device=dev) < 0.05).float() * 10.0
@@ -160,33 +164,32 @@ def run_b200(args):
         for w0 in range(0, len(my), pairs_per_wave):
             wave = my[w0:w0 + pairs_per_wave]
             npw = len(wave)
-            # split the wave's pairs over the two half tables
-            cut = (npw + 1) // 2
-            parts = [wave[:cut], wave[cut:]]
-            for h in range(2):
+            per = -(-npw // NS)                                   # pairs per stream partition
+            parts = [wave[h * per:(h + 1) * per] for h in range(NS)]
+            for h in range(NS):
                 k = len(parts[h])
-                act = np.zeros(half, dtype=np.uint8)
+                act = np.zeros(part, dtype=np.uint8)
                 act[:2 * k] = 1
-                ii = np.zeros(half, dtype=np.int64)
+                ii = np.zeros(part, dtype=np.int64)
                 ii[:2 * k] = np.repeat(parts[h], 2)
-                sc = np.tile([SIGMA, -SIGMA], half // 2).astype(np.float32)
-                sfs[h].set_slots(ii, sc, active=act if 2 * k < half else None)
+                sc = np.tile([SIGMA, -SIGMA], part // 2).astype(np.float32)
+                sfs[h].set_slots(ii, sc, active=act if 2 * k < part else None)
             ret_acc.zero_()
             for s in streams:
                 s.wait_stream(cur)
             for t in range(T):
                 blk = pool[t % R]
-                for h in range(2):
+                for h in range(NS):
                     if len(parts[h]) == 0:
                         continue
                     tally["launches"] += 1
                     tally["pairs"] += len(parts[h])
                     with torch.cuda.stream(streams[h]):
-                        sfs[h].forward(upd.theta, blk[h * half:(h + 1) * half], paired=True)
-                        ret_acc[h * half:(h + 1) * half] += rew_pool[t % 64, h * half:(h + 1) * half]
+                        sfs[h].forward(upd.theta, blk[h * part:(h + 1) * part], paired=True)
+                        ret_acc[h * part:(h + 1) * part] += rew_pool[t % 64, h * part:(h + 1) * part]
             for s in streams:
                 cur.wait_stream(s)
-            r = torch.cat([ret_acc[:2 * cut], ret_acc[half:half + 2 * (npw - cut)]]).view(-1, 2)
+            r = torch.cat([ret_acc[h * part:h * part + 2 * len(parts[h])] for h in range(NS)]).view(-1, 2)
             returns[w0:w0 + npw] = r
         allret = shard.all_gather_rows(returns, n_pairs)
         proc, _ = upd.centered_ranks(allret)
@@ -324,20 +327,27 @@ def cpu_baseline(args, noise_host):
     n_pairs = cores                                                  # one pair per worker process
     idx = rs.randint(0, len(noise_host) - P + 1, size=n_pairs).astype(np.int64)
     Ts = args.cpu_sample_steps
-    steps, wall, busy = W.measure_workers(NET, noise_host, theta, list(idx), Ts, SIGMA, cores)
-    # master update on a bounded sample of slices, scaled to n = pop/2
+    steps, wall, t_setup, t_step = W.measure_workers(NET, noise_host, theta, list(idx), Ts, SIGMA, cores)
+    gen_s, upd_full, n_upd = _cpu_generation_seconds(args, W, noise_host, theta, rs, cores, t_setup, t_step)
+    return {"value": args.pop * args.episode_len / gen_s, "unit": "env-steps/s", "cores": cores, "kind": "port",
+            "sample": f"{n_pairs} antithetic pairs x {Ts} env steps on {cores} forked 1-thread workers "
+                      f"({steps} steps in {wall:.1f}s wall; {t_step * 1e3:.2f} ms/env-step, {t_setup * 1e3:.1f} ms set-up per "
+                      f"episode, extrapolated to T={args.episode_len}) + master update on {n_upd} slices scaled to {args.pop // 2}",
+            "ms_per_env_step_per_core": t_step * 1e3, "setup_ms_per_episode": t_setup * 1e3,
+            "master_update_s_per_generation": upd_full, "generation_wall_clock_s": gen_s}
+
+
+def _cpu_generation_seconds(args, W, noise_host, theta, rs, cores, t_setup, t_step):
+    """Extrapolate the bounded sample to one full generation: pop episodes of T steps spread over `cores` workers
+    (set-up once per episode) + the single-process master update (es.py:273-301) measured on 50 slices."""
+    P = theta.size
     n_upd = 50
     uidx = rs.randint(0, len(noise_host) - P + 1, size=n_upd).astype(np.int64)
     ret = rs.permutation(2 * n_upd).astype(np.float32).reshape(n_upd, 2)
     upd_s, _ = W.measure_master_update(noise_host, theta, uidx, ret)
     upd_full = upd_s * (args.pop // 2) / n_upd
-    rollout_rate = steps / wall
-    gen_s = args.pop * args.episode_len / rollout_rate + upd_full
-    return {"value": args.pop * args.episode_len / gen_s, "unit": "env-steps/s", "cores": cores, "kind": "port",
-            "sample": f"{n_pairs} antithetic pairs x {Ts} env steps on {cores} forked 1-thread workers "
-                      f"({steps} steps in {wall:.1f}s) + master update on {n_upd} slices scaled to {args.pop // 2}",
-            "rollout_env_steps_per_s": rollout_rate, "master_update_s_per_generation": upd_full,
-            "generation_wall_clock_s": gen_s}
+    rollout_s = args.pop * (t_setup + args.episode_len * t_step) / cores
+    return rollout_s + upd_full, upd_full, n_upd
 
 
 def run_reference(args):
@@ -359,14 +369,11 @@ def run_reference(args):
     vals, times = [], []
     for it in range(args.warmup + args.steps):
         idx = rs.randint(0, len(noise_host) - P + 1, size=cores).astype(np.int64)
-        steps, wall, _ = W.measure_workers(NET, noise_host, theta, list(idx), Ts, SIGMA, cores, seed=it)
-        uidx = rs.randint(0, len(noise_host) - P + 1, size=n_upd).astype(np.int64)
-        ret = rs.permutation(2 * n_upd).astype(np.float32).reshape(n_upd, 2)
-        upd_s, _ = W.measure_master_update(noise_host, theta, uidx, ret)
-        gen_s = args.pop * args.episode_len / (steps / wall) + upd_s * (args.pop // 2) / n_upd
+        steps, wall, t_setup, t_step = W.measure_workers(NET, noise_host, theta, list(idx), Ts, SIGMA, cores, seed=it)
+        gen_s, _, _ = _cpu_generation_seconds(args, W, noise_host, theta, rs, cores, t_setup, t_step)
         if it >= args.warmup:
             vals.append(args.pop * args.episode_len / gen_s)
-            times.append(wall + upd_s)
+            times.append(wall)
     v = float(np.mean(vals))
     sample = (f"per step: {cores} antithetic pairs x {Ts} env steps on {cores} forked 1-thread workers + master update "
               f"on {n_upd} slices scaled to {args.pop // 2}; generation time extrapolated to pop {args.pop} x T {args.episode_len}")

@@ -64,6 +64,14 @@ extern "C" int dne_ctx_destroy(dne_ctx* ctx) {
     return DNE_OK;
 }
 
+// Runtime switches: "conv_tc" (1 = tcgen05 convolutions [default], 0 = fp32 SIMT convolutions).
+extern "C" int dne_set_option(const char* name, int value) {
+    DNE_CHECK_ARG(name, "name is null");
+    if (strcmp(name, "conv_tc") == 0) { g_dne_conv_tc = value ? 1 : 0; return DNE_OK; }
+    dne_set_error("dne_set_option: unknown option '%s'", name);
+    return DNE_ERR_ARG;
+}
+
 // ---- measurement hooks -------------------------------------------------------------------------------
 extern "C" long long dne_launch_count(int reset) {
     const long long v = (long long)g_dne_launches;

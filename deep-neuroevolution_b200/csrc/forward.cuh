@@ -25,6 +25,16 @@ struct DensePlan {
     size_t part_theta_floats, part_noise_floats;
 };
 
+extern int g_dne_conv_tc;
+int dne_launch_conv_layer_tc(const SlotArgs& sa, const dne_layer_desc& L, const LayerEpi& epi, bool in_u8,
+                             const void* in, int64_t in_slot_stride, int64_t in_img_stride, float* out,
+                             int64_t out_slot_stride, int64_t out_img_stride, int n_slots, int n_img,
+                             cudaStream_t st);
+int dne_launch_conv_layer_simt(const SlotArgs& sa, const dne_layer_desc& L, const LayerEpi& epi, bool in_u8,
+                               const void* in, int64_t in_slot_stride, int64_t in_img_stride, float* out,
+                               int64_t out_slot_stride, int64_t out_img_stride, int n_slots, int n_img,
+                               cudaStream_t st);
+
 DensePlan dne_plan_dense(const dne_layer_desc& L, int n_slots, int paired, bool shared_theta, int sm_count);
 
 int dne_launch_conv_layer(const SlotArgs& sa, const dne_layer_desc& L, const LayerEpi& epi, bool in_u8,

@@ -16,40 +16,7 @@
 // (+s, -s on the same slice) reads the slice ONCE for both members.
 #include "common.cuh"
 #include "forward.cuh"
-
-__device__ __forceinline__ bool slot_active(const SlotArgs& a, int slot) { return !a.active || a.active[slot]; }
-__device__ __forceinline__ const float* slot_theta(const SlotArgs& a, int slot) {
-    return a.theta + (a.theta_idx ? (int64_t)a.theta_idx[slot] * a.P : 0);
-}
-// member weight, exactly as the reference materialises it (es.py:413-419): v = fl(s*n); w = fl(theta + v)
-__device__ __forceinline__ float perturbed(float th, float s, float n) { return __fadd_rn(th, __fmul_rn(s, n)); }
-
-// per-output-channel affine (bias, batch-norm) + activation for one slot
-struct ChanEpi {
-    float bias, mean, inv, gamma, beta;
-    int bn, act;
-    __device__ __forceinline__ float apply(float acc) const {
-        float y = acc + bias;
-        if (bn == DNE_BN_TF) y = (y - mean) * inv * gamma + beta;   // policies.py:322 (eps 1e-3, decay 0)
-        return apply_act(y, act);
-    }
-};
-__device__ __forceinline__ ChanEpi make_chan_epi(const SlotArgs& sa, const LayerEpi& e, int slot, int cout, int n,
-                                                 const float* th, int64_t idx, float s) {
-    ChanEpi c;
-    c.bn = e.bn;
-    c.act = e.act;
-    c.bias = (e.off_b >= 0) ? perturbed(th[e.off_b + n], s, sa.noise[idx + e.off_b + n]) : 0.0f;
-    c.mean = 0.f; c.inv = 1.f; c.gamma = 1.f; c.beta = 0.f;
-    if (e.bn == DNE_BN_TF) {
-        const float* st = e.vbn + (int64_t)slot * e.vbn_len + e.bn_off;
-        c.mean = st[n];
-        c.inv = __fdiv_rn(1.0f, __fsqrt_rn(st[cout + n] + 1e-3f));
-        c.gamma = perturbed(th[e.off_gamma + n], s, sa.noise[idx + e.off_gamma + n]);
-        c.beta = perturbed(th[e.off_beta + n], s, sa.noise[idx + e.off_beta + n]);
-    }
-    return c;
-}
+#include "epilogue.cuh"
 
 // ---------------------------------------------------------------------------------------------------
 // Convolution as implicit GEMM, one member per blockIdx.y, BM output positions per CTA.
@@ -516,7 +483,22 @@ static bool conv_is(const dne_layer_desc& L, int cin, int cout, int ks, int stri
 }
 
 // in_u8: the layer reads uint8 observations.  Returns 0 or DNE_ERR_UNSUP.
+int g_dne_conv_tc = 1;     // 1: tcgen05 path (tc_conv.cu), 0: fp32 SIMT path (dne_set_option("conv_tc", v))
+
 int dne_launch_conv_layer(const SlotArgs& sa, const dne_layer_desc& L, const LayerEpi& epi, bool in_u8,
+                          const void* in, int64_t in_slot_stride, int64_t in_img_stride, float* out,
+                          int64_t out_slot_stride, int64_t out_img_stride, int n_slots, int n_img,
+                          cudaStream_t st) {
+    if (g_dne_conv_tc) {
+        const int rc = dne_launch_conv_layer_tc(sa, L, epi, in_u8, in, in_slot_stride, in_img_stride, out,
+                                                out_slot_stride, out_img_stride, n_slots, n_img, st);
+        if (rc != DNE_ERR_UNSUP) return rc;
+    }
+    return dne_launch_conv_layer_simt(sa, L, epi, in_u8, in, in_slot_stride, in_img_stride, out, out_slot_stride,
+                                      out_img_stride, n_slots, n_img, st);
+}
+
+int dne_launch_conv_layer_simt(const SlotArgs& sa, const dne_layer_desc& L, const LayerEpi& epi, bool in_u8,
                           const void* in, int64_t in_slot_stride, int64_t in_img_stride, float* out,
                           int64_t out_slot_stride, int64_t out_img_stride, int n_slots, int n_img,
                           cudaStream_t st) {

@@ -1,0 +1,111 @@
+// tc05.cuh -- minimal tcgen05 / TMEM / mbarrier PTX wrappers for sm_100a (hand-written; no CUTLASS dependency).
+//
+// Operand layout used throughout (UMMA "K-major, no swizzle / interleave" canonical layout, 32-bit elements):
+// a tile of R rows x KC k-elements is stored as float4 T[KC/4][R]:  element (r, k) lives at byte
+//     (k/4) * (R*16)  +  r*16  +  (k%4)*4
+// i.e. core matrices of 8 rows x 16 bytes are contiguous (128 B), the next 8-row group follows at SBO = 128 B and the
+// next 4 k-elements at LBO = R*16 B.  One tcgen05.mma kind::tf32 consumes K = 8 elements = two such k-quads.
+// Consecutive rows are consecutive 16-byte chunks, so staging threads that own consecutive rows write conflict-free.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace tc05 {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// ---- mbarrier ----------------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t a = smem_u32(bar);
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+        "@P1 bra DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "DONE:\n\t"
+        "}\n" ::"r"(a), "r"(parity)
+        : "memory");
+}
+
+// ---- fences ------------------------------------------------------------------------------------------
+// generic-proxy shared-memory writes -> visible to the async proxy (tensor core operand reads)
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_before_thread_sync() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_after_thread_sync() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// ---- TMEM allocation (one full warp) -----------------------------------------------------------------
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(ncols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+
+// ---- descriptors -------------------------------------------------------------------------------------
+// shared-memory matrix descriptor (sm_100 version 1), K-major, SWIZZLE_NONE
+__device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;          // descriptor version (Blackwell)
+    return d;                        // base_offset 0, lbo_mode 0, layout_type 0 (no swizzle)
+}
+// instruction descriptor: kind::tf32, fp32 accumulate, A and B K-major, dense
+__host__ __device__ constexpr uint32_t idesc_tf32(int M, int N) {
+    return (1u << 4)                      // c_format = F32
+           | (2u << 7) | (2u << 10)       // a_format = b_format = TF32
+           | ((uint32_t)(N >> 3) << 17)   // n_dim
+           | ((uint32_t)(M >> 4) << 24);  // m_dim
+}
+
+// D[tmem] (+)= A[smem] * B[smem]^T, issued by ONE thread
+__device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// all previously issued MMAs of this thread arrive on the mbarrier when complete (implies fence::before_thread_sync)
+__device__ __forceinline__ void mma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// ---- TMEM -> registers: this warp's 32 lanes x 16 consecutive fp32 columns ------------------------------
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// ---- 3xTF32 operand split ---------------------------------------------------------------------------
+// hi = rna_tf32(x), lo = rna_tf32(x - hi): both have their low 13 mantissa bits clear, so the tensor core's fp32->tf32
+// input truncation is exact.  a*b ~= hi_a*hi_b + lo_a*hi_b + hi_a*lo_b  (dropped lo*lo term ~2^-24 relative).
+__device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
+    uint32_t h;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(x));
+    hi = __uint_as_float(h);
+    uint32_t l;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(x - hi));
+    lo = __uint_as_float(l);
+}
+
+}  // namespace tc05

@@ -1,0 +1,343 @@
+// tc_conv.cu -- the member convolutions on the 5th-gen tensor cores (tcgen05.mma kind::tf32, accumulators in TMEM).
+//
+// Same contraction as conv_kernel in forward_kernels.cu (implicit GEMM, one member per CTA):
+//   A[m][k] = im2col(input)            m = output position, k = (ky,kx,ci)      (TF SAME, NHWC)
+//   B[n][k] = theta_w[k][n] + s*noise[idx+off_w+k*COUT+n]   (member weights, built by the perturb stage)
+//   D[m][n] = sum_k A*B  -> +bias (+virtual BN) -> relu -> NHWC store
+// fp32 parity on tensor cores: 3xTF32 -- every operand is split into hi + lo TF32 halves by the staging threads
+// (round-to-nearest, so the hardware's fp32->tf32 truncation is exact) and D += Ahi*Bhi + Alo*Bhi + Ahi*Blo.
+// Operands are PRODUCED into shared memory by the perturb / im2col stage (they do not exist in global memory, so
+// there is nothing for TMA to fetch); the layout is the UMMA K-major no-swizzle canonical layout (tc05.cuh).
+// One thread issues the MMAs of k-chunk c while all threads stage chunk c+1 (two smem stages, mbarrier-tracked by
+// tcgen05.commit); the 8 warps then drain TMEM with tcgen05.ld for the fused epilogue.
+#include "common.cuh"
+#include "forward.cuh"
+#include "epilogue.cuh"
+#include "tc05.cuh"
+
+using namespace tc05;
+
+constexpr int TC_THREADS = 256;
+
+template <int CIN, int COUT, int KS, int STRIDE, int HIN, int HOUT, int PAD, bool IN_U8, int MTC, int KC>
+struct TcConvCfg {
+    static constexpr int M = HOUT * HOUT;
+    static constexpr int K = KS * KS * CIN;
+    static constexpr int ROWS = MTC * 128;                       // A rows staged per CTA
+    static constexpr int NCHUNK = K / KC;
+    static constexpr int A_PLANE = ROWS * 16;                    // bytes per k-quad plane of A (= LBO of A)
+    static constexpr int B_PLANE = COUT * 16;                    // bytes per k-quad plane of B (= LBO of B)
+    static constexpr int A_BYTES = (KC / 4) * A_PLANE;           // one of {hi, lo}
+    static constexpr int B_BYTES = (KC / 4) * B_PLANE;
+    static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+    static constexpr int SMEM_BYTES = 2 * STAGE_BYTES + 128;     // + alignment slack
+    static constexpr int TMEM_COLS = (MTC * COUT <= 32) ? 32 : (MTC * COUT <= 64) ? 64 : (MTC * COUT <= 128) ? 128 : 256;
+    static_assert(K % KC == 0 && KC % 8 == 0 && CIN % 4 == 0 && COUT % 16 == 0, "tile constraints");
+};
+
+template <int CIN, int COUT, int KS, int STRIDE, int HIN, int HOUT, int PAD, bool IN_U8, int MTC, int KC>
+__global__ void __launch_bounds__(TC_THREADS)
+conv_tc_kernel(SlotArgs sa, int64_t off_w, LayerEpi epi, const void* __restrict__ in_base, int64_t in_slot_stride,
+               int64_t in_img_stride, float* __restrict__ out_base, int64_t out_slot_stride, int64_t out_img_stride) {
+    using Cfg = TcConvCfg<CIN, COUT, KS, STRIDE, HIN, HOUT, PAD, IN_U8, MTC, KC>;
+    const int slot = blockIdx.y;
+    if (!slot_active(sa, slot)) return;
+    const int img = blockIdx.z;
+    const int row0 = blockIdx.x * Cfg::ROWS;                     // first output position of this CTA
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
+    __shared__ uint64_t bars[2];
+    __shared__ uint32_t tmem_base_s;
+
+    if (warp == 0) tmem_alloc(&tmem_base_s, Cfg::TMEM_COLS);
+    if (tid == 32) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        fence_mbar_init();
+    }
+    fence_before_thread_sync();
+    __syncthreads();
+    fence_after_thread_sync();
+    const uint32_t tmem_base = tmem_base_s;
+
+    const float* th = slot_theta(sa, slot);
+    const int64_t idx = sa.noise_idx[slot];
+    const float s = sa.scale[slot];
+    const float* nz = sa.noise + idx + off_w;
+    const float* tw = th + off_w;
+    const uint8_t* in_u8 = nullptr;
+    const float* in_f = nullptr;
+    if (IN_U8) in_u8 = (const uint8_t*)in_base + slot * in_slot_stride + img * in_img_stride;
+    else in_f = (const float*)in_base + slot * in_slot_stride + img * in_img_stride;
+
+    // A staging units of this thread: (row r, k-quad q), r fastest.  r is fixed per unit index across chunks.
+    constexpr int A_UNITS = Cfg::ROWS * (KC / 4);
+    constexpr int A_PER_THREAD = A_UNITS / TC_THREADS;
+    static_assert(A_UNITS % TC_THREADS == 0 && Cfg::ROWS % TC_THREADS == 0 || TC_THREADS % Cfg::ROWS == 0, "A staging map");
+    int a_iy0[A_PER_THREAD], a_ix0[A_PER_THREAD];
+    bool a_ok[A_PER_THREAD];
+#pragma unroll
+    for (int i = 0; i < A_PER_THREAD; ++i) {
+        const int u = tid + i * TC_THREADS;
+        const int m = row0 + (u % Cfg::ROWS);
+        a_ok[i] = m < Cfg::M;
+        a_iy0[i] = (m / HOUT) * STRIDE - PAD;
+        a_ix0[i] = (m % HOUT) * STRIDE - PAD;
+    }
+    constexpr int B_UNITS = COUT * (KC / 4);
+    constexpr int B_PER_THREAD = (B_UNITS + TC_THREADS - 1) / TC_THREADS;
+
+    constexpr uint32_t IDESC = idesc_tf32(128, COUT);
+
+    for (int c = 0; c < Cfg::NCHUNK; ++c) {
+        const int st = c & 1;
+        if (c >= 2) mbar_wait(&bars[st], ((c >> 1) - 1) & 1);     // MMAs of chunk c-2 finished reading this stage
+        uint8_t* sA_hi = smem + st * Cfg::STAGE_BYTES;
+        uint8_t* sA_lo = sA_hi + Cfg::A_BYTES;
+        uint8_t* sB_hi = sA_lo + Cfg::A_BYTES;
+        uint8_t* sB_lo = sB_hi + Cfg::B_BYTES;
+        const int k0 = c * KC;
+        // ---- stage A: im2col gather + hi/lo split ----
+#pragma unroll
+        for (int i = 0; i < A_PER_THREAD; ++i) {
+            const int u = tid + i * TC_THREADS;
+            const int r = u % Cfg::ROWS, q = u / Cfg::ROWS;
+            const int k = k0 + 4 * q;
+            const int ci = k % CIN, t = k / CIN;
+            const int kx = t % KS, ky = t / KS;
+            const int iy = a_iy0[i] + ky, ix = a_ix0[i] + kx;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (a_ok[i] && iy >= 0 && iy < HIN && ix >= 0 && ix < HIN) {
+                const int e = (iy * HIN + ix) * CIN + ci;
+                if (IN_U8) {
+                    const uchar4 p = *reinterpret_cast<const uchar4*>(in_u8 + e);
+                    v.x = __fdiv_rn((float)p.x, 255.0f);
+                    v.y = __fdiv_rn((float)p.y, 255.0f);
+                    v.z = __fdiv_rn((float)p.z, 255.0f);
+                    v.w = __fdiv_rn((float)p.w, 255.0f);
+                } else {
+                    v = *reinterpret_cast<const float4*>(in_f + e);
+                }
+            }
+            float4 hi, lo;
+            split_tf32(v.x, hi.x, lo.x);
+            split_tf32(v.y, hi.y, lo.y);
+            split_tf32(v.z, hi.z, lo.z);
+            split_tf32(v.w, hi.w, lo.w);
+            *reinterpret_cast<float4*>(sA_hi + q * Cfg::A_PLANE + r * 16) = hi;
+            *reinterpret_cast<float4*>(sA_lo + q * Cfg::A_PLANE + r * 16) = lo;
+        }
+        // ---- stage B: member weights, transposed to [n][k] quads + hi/lo split ----
+#pragma unroll
+        for (int i = 0; i < B_PER_THREAD; ++i) {
+            const int u = tid + i * TC_THREADS;
+            if (u < B_UNITS) {
+                const int n = u % COUT, q = u / COUT;
+                const int64_t f = (int64_t)(k0 + 4 * q) * COUT + n;
+                float4 w;
+                w.x = perturbed(tw[f], s, nz[f]);
+                w.y = perturbed(tw[f + COUT], s, nz[f + COUT]);
+                w.z = perturbed(tw[f + 2 * COUT], s, nz[f + 2 * COUT]);
+                w.w = perturbed(tw[f + 3 * COUT], s, nz[f + 3 * COUT]);
+                float4 hi, lo;
+                split_tf32(w.x, hi.x, lo.x);
+                split_tf32(w.y, hi.y, lo.y);
+                split_tf32(w.z, hi.z, lo.z);
+                split_tf32(w.w, hi.w, lo.w);
+                *reinterpret_cast<float4*>(sB_hi + q * Cfg::B_PLANE + n * 16) = hi;
+                *reinterpret_cast<float4*>(sB_lo + q * Cfg::B_PLANE + n * 16) = lo;
+            }
+        }
+        fence_proxy_async_smem();          // generic-proxy writes -> async proxy (tensor core reads)
+        __syncthreads();
+        if (tid == 0) {
+            fence_after_thread_sync();
+            const uint32_t aH = smem_u32(sA_hi), aL = smem_u32(sA_lo), bH = smem_u32(sB_hi), bL = smem_u32(sB_lo);
+#pragma unroll
+            for (int mt = 0; mt < MTC; ++mt) {
+                const uint32_t d = tmem_base + mt * COUT;
+#pragma unroll
+                for (int k8 = 0; k8 < KC / 8; ++k8) {
+                    const uint32_t ao = 2 * k8 * Cfg::A_PLANE + mt * 128 * 16;
+                    const uint32_t bo = 2 * k8 * Cfg::B_PLANE;
+                    const uint64_t dAh = smem_desc(aH + ao, Cfg::A_PLANE, 128), dAl = smem_desc(aL + ao, Cfg::A_PLANE, 128);
+                    const uint64_t dBh = smem_desc(bH + bo, Cfg::B_PLANE, 128), dBl = smem_desc(bL + bo, Cfg::B_PLANE, 128);
+                    mma_tf32(d, dAh, dBh, IDESC, (c | k8) != 0);
+                    mma_tf32(d, dAl, dBh, IDESC, 1);
+                    mma_tf32(d, dAh, dBl, IDESC, 1);
+                }
+            }
+            mma_commit(&bars[st]);
+        }
+    }
+    // the last commit covers every MMA issued before it
+    {
+        constexpr int last = Cfg::NCHUNK - 1;
+        mbar_wait(&bars[last & 1], (last >> 1) & 1);
+    }
+    fence_after_thread_sync();
+
+    // ---- epilogue: TMEM -> registers -> bias (+BN) + activation -> NHWC global ----
+    float* out = out_base + slot * out_slot_stride + img * out_img_stride;
+    const int lg = warp & 3, ch = warp >> 2;                      // TMEM lane group of this warp; column-group parity
+#pragma unroll
+    for (int j = 0; j < COUT / 16; ++j) {
+        if ((j & 1) != ch && COUT > 16) continue;                 // warps w and w+4 share lanes: split the column groups
+        if (COUT == 16 && ch != 0) continue;
+        const int n0 = j * 16;
+        ChanEpi ce[16];
+#pragma unroll
+        for (int x = 0; x < 16; ++x) ce[x] = make_chan_epi(sa, epi, slot, COUT, n0 + x, th, idx, s);
+#pragma unroll
+        for (int mt = 0; mt < MTC; ++mt) {
+            float v[16];
+            tmem_ld16(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(mt * COUT + n0), v);
+            const int m = row0 + mt * 128 + lg * 32 + lane;
+            if (m < Cfg::M) {
+                float4* dst = reinterpret_cast<float4*>(out + (int64_t)m * COUT + n0);
+#pragma unroll
+                for (int x = 0; x < 16; x += 4)
+                    dst[x / 4] = make_float4(ce[x].apply(v[x]), ce[x + 1].apply(v[x + 1]), ce[x + 2].apply(v[x + 2]),
+                                             ce[x + 3].apply(v[x + 3]));
+            }
+        }
+    }
+    fence_before_thread_sync();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+}
+
+// =====================================================================================================
+template <int CIN, int COUT, int KS, int STRIDE, int HIN, int HOUT, int PAD, bool IN_U8, int MTC, int KC>
+static int launch_conv_tc(const SlotArgs& sa, const dne_layer_desc& L, const LayerEpi& epi, const void* in,
+                          int64_t in_slot_stride, int64_t in_img_stride, float* out, int64_t out_slot_stride,
+                          int64_t out_img_stride, int n_slots, int n_img, cudaStream_t st) {
+    using Cfg = TcConvCfg<CIN, COUT, KS, STRIDE, HIN, HOUT, PAD, IN_U8, MTC, KC>;
+    auto kern = conv_tc_kernel<CIN, COUT, KS, STRIDE, HIN, HOUT, PAD, IN_U8, MTC, KC>;
+    static bool attr_done = false;
+    if (!attr_done) {
+        if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES) != cudaSuccess)
+            return DNE_ERR_CUDA;
+        attr_done = true;
+    }
+    dim3 grid((Cfg::M + Cfg::ROWS - 1) / Cfg::ROWS, n_slots, n_img);
+    kern<<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(sa, L.off_w, epi, in, in_slot_stride, in_img_stride, out,
+                                                   out_slot_stride, out_img_stride);
+    DNE_LAUNCHED(1);
+    return 0;
+}
+
+static bool tconv_is(const dne_layer_desc& L, int cin, int cout, int ks, int stride, int hin, int hout, int pad) {
+    return L.cin == cin && L.cout == cout && L.ksize == ks && L.stride == stride && L.hin == hin &&
+           L.hout == hout && L.pad == pad;
+}
+
+int dne_launch_conv_layer_tc(const SlotArgs& sa, const dne_layer_desc& L, const LayerEpi& epi, bool in_u8,
+                             const void* in, int64_t in_slot_stride, int64_t in_img_stride, float* out,
+                             int64_t out_slot_stride, int64_t out_img_stride, int n_slots, int n_img,
+                             cudaStream_t st) {
+#define ARGS sa, L, epi, in, in_slot_stride, in_img_stride, out, out_slot_stride, out_img_stride, n_slots, n_img, st
+    if (in_u8 && tconv_is(L, 4, 32, 8, 4, 84, 21, 2)) return launch_conv_tc<4, 32, 8, 4, 84, 21, 2, true, 2, 16>(ARGS);
+    if (in_u8 && tconv_is(L, 4, 16, 8, 4, 84, 21, 2)) return launch_conv_tc<4, 16, 8, 4, 84, 21, 2, true, 2, 16>(ARGS);
+    if (!in_u8 && tconv_is(L, 32, 64, 4, 2, 21, 11, 1)) return launch_conv_tc<32, 64, 4, 2, 21, 11, 1, false, 1, 32>(ARGS);
+    if (!in_u8 && tconv_is(L, 16, 32, 4, 2, 21, 11, 1)) return launch_conv_tc<16, 32, 4, 2, 21, 11, 1, false, 1, 32>(ARGS);
+    if (!in_u8 && tconv_is(L, 64, 64, 3, 1, 11, 11, 1)) return launch_conv_tc<64, 64, 3, 1, 11, 11, 1, false, 1, 32>(ARGS);
+#undef ARGS
+    return DNE_ERR_UNSUP;
+}
+
+// =====================================================================================================
+// Self-test of the tcgen05 plumbing: C[128,N] = A[128,K] * B[N,K]^T with the same staging / descriptor / 3xTF32 code
+// path (single CTA).  Exposed through the C ABI for tests/test_gpu_parity.py.
+// =====================================================================================================
+template <int N>
+__global__ void __launch_bounds__(128) tc_gemm_test_kernel(const float* __restrict__ A, const float* __restrict__ B,
+                                                           float* __restrict__ C, int K) {
+    constexpr int KC = 32;
+    constexpr int A_PLANE = 128 * 16, B_PLANE = N * 16;
+    constexpr int TCOLS = N < 32 ? 32 : N;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
+    uint8_t* sA_hi = smem;
+    uint8_t* sA_lo = sA_hi + (KC / 4) * A_PLANE;
+    uint8_t* sB_hi = sA_lo + (KC / 4) * A_PLANE;
+    uint8_t* sB_lo = sB_hi + (KC / 4) * B_PLANE;
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tmem_base_s;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (warp == 0) tmem_alloc(&tmem_base_s, TCOLS);
+    if (tid == 32) { mbar_init(&bar, 1); fence_mbar_init(); }
+    fence_before_thread_sync();
+    __syncthreads();
+    fence_after_thread_sync();
+    const uint32_t tmem_base = tmem_base_s;
+    constexpr uint32_t IDESC = idesc_tf32(128, N);
+    int phase = 0;
+    for (int k0 = 0; k0 < K; k0 += KC) {
+        for (int u = tid; u < 128 * (KC / 4); u += 128) {
+            const int r = u % 128, q = u / 128;
+            const float4 v = *reinterpret_cast<const float4*>(A + (int64_t)r * K + k0 + 4 * q);
+            float4 hi, lo;
+            split_tf32(v.x, hi.x, lo.x); split_tf32(v.y, hi.y, lo.y); split_tf32(v.z, hi.z, lo.z); split_tf32(v.w, hi.w, lo.w);
+            *reinterpret_cast<float4*>(sA_hi + q * A_PLANE + r * 16) = hi;
+            *reinterpret_cast<float4*>(sA_lo + q * A_PLANE + r * 16) = lo;
+        }
+        for (int u = tid; u < N * (KC / 4); u += 128) {
+            const int n = u % N, q = u / N;
+            const float4 v = *reinterpret_cast<const float4*>(B + (int64_t)n * K + k0 + 4 * q);
+            float4 hi, lo;
+            split_tf32(v.x, hi.x, lo.x); split_tf32(v.y, hi.y, lo.y); split_tf32(v.z, hi.z, lo.z); split_tf32(v.w, hi.w, lo.w);
+            *reinterpret_cast<float4*>(sB_hi + q * B_PLANE + n * 16) = hi;
+            *reinterpret_cast<float4*>(sB_lo + q * B_PLANE + n * 16) = lo;
+        }
+        fence_proxy_async_smem();
+        __syncthreads();
+        if (tid == 0) {
+            fence_after_thread_sync();
+            for (int k8 = 0; k8 < KC / 8; ++k8) {
+                const uint64_t dAh = smem_desc(smem_u32(sA_hi) + 2 * k8 * A_PLANE, A_PLANE, 128);
+                const uint64_t dAl = smem_desc(smem_u32(sA_lo) + 2 * k8 * A_PLANE, A_PLANE, 128);
+                const uint64_t dBh = smem_desc(smem_u32(sB_hi) + 2 * k8 * B_PLANE, B_PLANE, 128);
+                const uint64_t dBl = smem_desc(smem_u32(sB_lo) + 2 * k8 * B_PLANE, B_PLANE, 128);
+                mma_tf32(tmem_base, dAh, dBh, IDESC, (k0 | k8) != 0);
+                mma_tf32(tmem_base, dAl, dBh, IDESC, 1);
+                mma_tf32(tmem_base, dAh, dBl, IDESC, 1);
+            }
+            mma_commit(&bar);
+        }
+        mbar_wait(&bar, phase);            // synchronous version: wait before re-staging
+        phase ^= 1;
+    }
+    fence_after_thread_sync();
+#pragma unroll
+    for (int j = 0; j < N / 16; ++j) {
+        float v[16];
+        tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + j * 16, v);
+        const int m = warp * 32 + lane;
+#pragma unroll
+        for (int x = 0; x < 16; ++x) C[(int64_t)m * N + j * 16 + x] = v[x];
+    }
+    fence_before_thread_sync();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_base, TCOLS);
+}
+
+extern "C" int dne_test_tc_gemm(const float* d_A, const float* d_B, float* d_C, int K, int N, void* stream) {
+    DNE_CHECK_ARG(d_A && d_B && d_C && K > 0 && K % 32 == 0 && (N == 16 || N == 32 || N == 64), "bad arguments");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int smem = 2 * 8 * 128 * 16 + 2 * 8 * N * 16 + 128;
+    if (N == 16) {
+        DNE_CUDA(cudaFuncSetAttribute(tc_gemm_test_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        tc_gemm_test_kernel<16><<<1, 128, smem, st>>>(d_A, d_B, d_C, K);
+    } else if (N == 32) {
+        DNE_CUDA(cudaFuncSetAttribute(tc_gemm_test_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        tc_gemm_test_kernel<32><<<1, 128, smem, st>>>(d_A, d_B, d_C, K);
+    } else {
+        DNE_CUDA(cudaFuncSetAttribute(tc_gemm_test_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        tc_gemm_test_kernel<64><<<1, 128, smem, st>>>(d_A, d_B, d_C, K);
+    }
+    DNE_LAUNCH_CHECK1();
+    return DNE_OK;
+}

@@ -91,6 +91,11 @@ int         dne_abi_sizes(int* layer_desc_bytes, int* net_desc_bytes);
  * dne_profile_enable/read: CUDA-event timing of every launch of the dominant HBM-bound kernel
  * (dense_noise_gemv) on the stream it is launched on; read() synchronises the device. */
 long long   dne_launch_count(int reset);
+/* Runtime switches: "conv_tc" = 1 (default) runs the member convolutions on the tensor cores (tcgen05.mma kind::tf32,
+ * 3xTF32 split, TMEM accumulators); 0 selects the fp32 SIMT convolution kernels (kept for A/B parity checks). */
+int         dne_set_option(const char* name, int value);
+/* Self-test of the tcgen05 plumbing: C[128,N] = A[128,K] * B[N,K]^T (row-major, K % 32 == 0, N in {16,32,64}). */
+int         dne_test_tc_gemm(const float* d_A, const float* d_B, float* d_C, int K, int N, void* stream);
 int         dne_profile_enable(dne_ctx* ctx, int on, int capacity);
 int         dne_profile_read(dne_ctx* ctx, int* n_launches, double* total_ms);
 

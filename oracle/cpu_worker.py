@@ -86,30 +86,40 @@ def _worker(args):
     obs_pool = rs.randint(0, 256, size=(16, 1, 84, 84, 4)).astype(np.uint8)
     ref = _G.get("ref_batch")
     steps, out = 0, []
-    t0 = time.perf_counter()
+    t_setup = t_steps = 0.0
     for idx in pair_idx:
+        ta = time.perf_counter()
         v = np.float32(sigma) * noise[idx:idx + net.num_params]              # es.py:413
+        t_setup += time.perf_counter() - ta
         rets = []
         for sign in (+1, -1):
+            ta = time.perf_counter()
             prep = prepare(net, (theta + v) if sign > 0 else (theta - v))   # es.py:415,419
             stats = None
             if ref is not None:
                 _, stats = forward_prepared(net, prep, ref, is_ref=True)     # policies.py:399
+            tb = time.perf_counter()
+            t_setup += tb - ta
             ret = 0.0
             for t in range(T):                                               # policies.py:401-424
                 logits, _ = forward_prepared(net, prep, obs_pool[t & 15], vbn_stats=stats)
                 _ = int(torch.argmax(logits, dim=1)[0])
                 ret += 10.0 * float(rs.random_sample() < 0.05)               # stub env.step
                 steps += 1
+            t_steps += time.perf_counter() - tb
             rets.append(ret)
         out.append(rets)
-    return steps, time.perf_counter() - t0, out
+    return steps, t_setup, t_steps, out
 
 
 def measure_workers(net_name: str, noise: np.ndarray, theta: np.ndarray, idx: List[int], T: int, sigma: float,
                     n_workers: int, use_ref_batch: bool = False, seed: int = 0):
-    """Fork `n_workers` processes (noise shared by fork), split `idx` among them, return
-    (total env steps, wall seconds, per-worker busy seconds)."""
+    """Fork `n_workers` processes (noise shared by fork), split `idx` among them.  Returns
+    (total env steps, wall seconds, per-episode set-up seconds [set_trainable_flat (+ VBN pass)], per-env-step
+    seconds) -- the last two are busy-time averages over all workers, used to extrapolate the bounded sample to
+    full-length episodes (set-up is paid once per episode)."""
+    import torch                      # import in the parent so the forked workers do not each pay the cold import
+    torch.set_num_threads(1)
     net = O.make_net(net_name)
     _G.update(net=net, noise=noise, theta=theta)
     if use_ref_batch:
@@ -123,7 +133,9 @@ def measure_workers(net_name: str, noise: np.ndarray, theta: np.ndarray, idx: Li
     with ctx.Pool(len(chunks)) as pool:
         res = pool.map(_worker, [(w, c, T, sigma, seed) for w, c in enumerate(chunks)])
     wall = time.perf_counter() - t0
-    return sum(r[0] for r in res), wall, [r[1] for r in res]
+    steps = sum(r[0] for r in res)
+    episodes = 2 * sum(len(c) for c in chunks)
+    return steps, wall, sum(r[1] for r in res) / episodes, sum(r[2] for r in res) / max(steps, 1)
 
 
 def measure_master_update(noise: np.ndarray, theta: np.ndarray, idx: np.ndarray, returns_n2: np.ndarray,

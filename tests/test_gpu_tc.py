@@ -1,0 +1,132 @@
+"""GPU tests of the tensor-core (tcgen05 / TMEM, 3xTF32) convolution path against the oracle and against the
+fp32 SIMT path, plus GA slots (per-slot parent rows) and a self-test of the tcgen05 plumbing."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+if not torch.cuda.is_available():
+    pytest.skip("needs a CUDA device", allow_module_level=True)
+
+from oracle import oracle as O            # noqa: E402
+from dne import _ffi as F                 # noqa: E402
+from dne import nets as N                 # noqa: E402
+from dne.engine import SlotForward, make_context   # noqa: E402
+from dne.noise import SharedNoiseTable    # noqa: E402
+
+DEV = torch.device("cuda", 0)
+NOISE_COUNT = 6_000_000
+
+
+@pytest.fixture(scope="module")
+def host_noise():
+    return O.noise_table(NOISE_COUNT)
+
+
+@pytest.fixture(scope="module")
+def ctx(host_noise):
+    return make_context(0, SharedNoiseTable(host_noise=host_noise, device=DEV))
+
+
+def cuda(x):
+    return torch.as_tensor(np.ascontiguousarray(x)).to(DEV).contiguous()
+
+
+@pytest.mark.parametrize("n,k", [(32, 256), (64, 512), (64, 576), (16, 256), (32, 32)])
+def test_tcgen05_gemm_selftest(n, k):
+    """C = A B^T through the hand-written tcgen05 path (smem descriptors, instruction descriptor, TMEM alloc/ld,
+    mbarrier commit) with the 3xTF32 split: must be fp32-accurate, not TF32-accurate."""
+    rs = np.random.RandomState(n * 1000 + k)
+    A = rs.randn(128, k).astype(np.float32)
+    B = rs.randn(n, k).astype(np.float32)
+    dA, dB = cuda(A), cuda(B)
+    dC = torch.full((128, n), float("nan"), dtype=torch.float32, device=DEV)
+    F.check(F.lib().dne_test_tc_gemm(F.ptr(dA), F.ptr(dB), F.ptr(dC), k, n, F.stream_ptr()))
+    got = dC.cpu().numpy()
+    ref = A.astype(np.float64) @ B.astype(np.float64).T
+    scale = np.abs(ref).max()
+    err = np.abs(got - ref).max()
+    assert err <= 2e-6 * scale, (err, scale)        # plain TF32 would be ~1e-3
+
+
+def _forward(ctx, net, theta, idx, scale, obs, paired, conv_tc, theta_idx=None):
+    F.check(F.lib().dne_set_option(b"conv_tc", conv_tc))
+    try:
+        sf = SlotForward(ctx, net, len(idx))
+        sf.set_slots(idx, scale, theta_idx=theta_idx)
+        d_theta, d_obs = cuda(theta), cuda(obs)
+        actions = sf.forward(d_theta, d_obs, paired=paired).cpu().numpy()
+        return sf.logits.cpu().numpy(), actions
+    finally:
+        F.check(F.lib().dne_set_option(b"conv_tc", 1))
+
+
+@pytest.mark.parametrize("name", ["LargeModel", "Model"])
+def test_conv_tc_vs_simt_vs_oracle(ctx, host_noise, name):
+    net, net_o = N.make_net(name), O.make_net(name)
+    P = net.num_params
+    rs = np.random.RandomState(5)
+    theta = (rs.randn(P) * 0.05).astype(np.float32)
+    n_slots = 6
+    pidx = rs.randint(0, NOISE_COUNT - P + 1, size=n_slots // 2).astype(np.int64)
+    idx, scale = np.repeat(pidx, 2), np.tile([0.02, -0.02], n_slots // 2).astype(np.float32)
+    obs = rs.randint(0, 256, size=(n_slots, 84, 84, 4)).astype(np.uint8)
+    lt, at = _forward(ctx, net, theta, idx, scale, obs, 1, 1)
+    ls, as_ = _forward(ctx, net, theta, idx, scale, obs, 1, 0)
+    ref = np.stack([O.forward(net_o, O.perturb(theta, host_noise, int(idx[s]), 0.02, 1 if scale[s] > 0 else -1),
+                              obs[s:s + 1])[0][0] for s in range(n_slots)])
+    bound = 2e-5 * max(1.0, float(np.abs(ref).max()))
+    assert np.abs(ls - ref).max() <= bound
+    assert np.abs(lt - ref).max() <= bound, np.abs(lt - ref).max()
+    srt = np.sort(ref, axis=1)
+    decided = (srt[:, -1] - srt[:, -2]) > 2 * bound
+    np.testing.assert_array_equal(at[decided], np.argmax(ref, axis=1)[decided])
+
+
+def test_conv_tc_intermediate_activations(ctx, host_noise):
+    """Layer-by-layer check of the tensor-core convolutions (conv3 output = the 7744-vector fed to the fc layer)."""
+    net, net_o = N.make_net("LargeModel"), O.make_net("LargeModel")
+    P = net.num_params
+    rs = np.random.RandomState(8)
+    theta = (rs.randn(P) * 0.05).astype(np.float32)
+    idx = np.array([17, 17], dtype=np.int64)
+    scale = np.array([0.02, -0.02], dtype=np.float32)
+    obs = rs.randint(0, 256, size=(2, 84, 84, 4)).astype(np.uint8)
+    sf = SlotForward(ctx, net, 2)
+    sf.set_slots(idx, scale)
+    d_theta, d_obs = cuda(theta), cuda(obs)
+    sf.forward(d_theta, d_obs, paired=True)
+    torch.cuda.synchronize()
+    ws = sf.ws.view(torch.float32)
+    off = 0
+    for li, l in enumerate(net.layers[:3]):
+        elems = l.out_elems
+        got = ws[off:off + 2 * elems].cpu().numpy().reshape(2, l.hout, l.hout, l.cout)
+        off += ((2 * elems * 4 + 255) // 256 * 256) // 4
+        for s in range(2):
+            th = O.perturb(theta, host_noise, 17, 0.02, 1 if s == 0 else -1)
+            acts = O.forward(net_o, th, obs[s:s + 1], return_all=True)[2]
+            want = acts[li][0]
+            assert np.abs(got[s] - want).max() <= 2e-5 * max(1.0, np.abs(want).max()), (li, s)
+
+
+@pytest.mark.parametrize("paired", [0, 2])
+def test_ga_slots_parent_rows(ctx, host_noise, paired):
+    """GA offspring: theta[parent(slot)] + power*noise[seed(slot)] (models/base.py:148-156), per-slot parent rows.
+    paired=2: slots (2p,2p+1) share the parent row (read once)."""
+    net, net_o = N.make_net("LargeModel"), O.make_net("LargeModel")
+    P = net.num_params
+    rs = np.random.RandomState(31)
+    parents = (rs.randn(3, P) * 0.05).astype(np.float32)
+    n_slots = 6
+    tidx = np.array([2, 2, 0, 0, 1, 1], dtype=np.int32) if paired == 2 else np.array([2, 0, 1, 1, 0, 2], dtype=np.int32)
+    idx = rs.randint(0, NOISE_COUNT - P + 1, size=n_slots).astype(np.int64)
+    scale = np.full(n_slots, 0.002, dtype=np.float32)
+    obs = rs.randint(0, 256, size=(n_slots, 84, 84, 4)).astype(np.uint8)
+    logits, actions = _forward(ctx, net, parents, idx, scale, obs, paired, 1, theta_idx=tidx)
+    ref = np.stack([O.forward(net_o, (parents[tidx[s]] + np.float32(0.002) * host_noise[idx[s]:idx[s] + P]).astype(np.float32),
+                              obs[s:s + 1])[0][0] for s in range(n_slots)])
+    bound = 2e-5 * max(1.0, float(np.abs(ref).max()))
+    assert np.abs(logits - ref).max() <= bound, np.abs(logits - ref).max()

@@ -182,8 +182,8 @@ def test_cpu_worker_sample_runs():
     net = O.make_net("Model")
     noise = O.noise_table(net.num_params + 10_000)
     theta = noise[:net.num_params].copy() * np.float32(0.05)
-    steps, wall, busy = W.measure_workers("Model", noise, theta, [3, 77], 4, 0.005, 2)
-    assert steps == 2 * 2 * 4 and wall > 0
+    steps, wall, t_setup, t_step = W.measure_workers("Model", noise, theta, [3, 77], 4, 0.005, 2)
+    assert steps == 2 * 2 * 4 and wall > 0 and t_setup > 0 and t_step > 0
     secs, g = W.measure_master_update(noise, theta, np.array([1, 5, 9]), np.arange(6, dtype=np.float32).reshape(3, 2))
     assert g.shape == (net.num_params,) and g.dtype == np.float32
 
