@@ -66,6 +66,33 @@ __device__ __forceinline__ float4 ldg_stream_f4(const float* p) {
                  : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
     return r;
 }
+// Eight independent streaming 128-bit loads issued back to back from ONE asm statement, so the compiler cannot
+// interleave them with their consumers: 8 x 16 B per thread are guaranteed to be in flight together (memory-level
+// parallelism is what an HBM-bound kernel lives on; ptxas otherwise serialises to ~3 loads in flight).
+__device__ __forceinline__ void ldg_stream_f4x8(const float* p, int64_t stride, float4 (&v)[8]) {
+    const float* p0 = p;
+    const float* p1 = p + stride;
+    const float* p2 = p + 2 * stride;
+    const float* p3 = p + 3 * stride;
+    const float* p4 = p + 4 * stride;
+    const float* p5 = p + 5 * stride;
+    const float* p6 = p + 6 * stride;
+    const float* p7 = p + 7 * stride;
+    asm volatile(
+        "ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%32];\n\t"
+        "ld.global.nc.L1::no_allocate.v4.f32 {%4,%5,%6,%7}, [%33];\n\t"
+        "ld.global.nc.L1::no_allocate.v4.f32 {%8,%9,%10,%11}, [%34];\n\t"
+        "ld.global.nc.L1::no_allocate.v4.f32 {%12,%13,%14,%15}, [%35];\n\t"
+        "ld.global.nc.L1::no_allocate.v4.f32 {%16,%17,%18,%19}, [%36];\n\t"
+        "ld.global.nc.L1::no_allocate.v4.f32 {%20,%21,%22,%23}, [%37];\n\t"
+        "ld.global.nc.L1::no_allocate.v4.f32 {%24,%25,%26,%27}, [%38];\n\t"
+        "ld.global.nc.L1::no_allocate.v4.f32 {%28,%29,%30,%31}, [%39];"
+        : "=f"(v[0].x), "=f"(v[0].y), "=f"(v[0].z), "=f"(v[0].w), "=f"(v[1].x), "=f"(v[1].y), "=f"(v[1].z), "=f"(v[1].w),
+          "=f"(v[2].x), "=f"(v[2].y), "=f"(v[2].z), "=f"(v[2].w), "=f"(v[3].x), "=f"(v[3].y), "=f"(v[3].z), "=f"(v[3].w),
+          "=f"(v[4].x), "=f"(v[4].y), "=f"(v[4].z), "=f"(v[4].w), "=f"(v[5].x), "=f"(v[5].y), "=f"(v[5].z), "=f"(v[5].w),
+          "=f"(v[6].x), "=f"(v[6].y), "=f"(v[6].z), "=f"(v[6].w), "=f"(v[7].x), "=f"(v[7].y), "=f"(v[7].z), "=f"(v[7].w)
+        : "l"(p0), "l"(p1), "l"(p2), "l"(p3), "l"(p4), "l"(p5), "l"(p6), "l"(p7));
+}
 __device__ __forceinline__ float ldg_stream_f1(const float* p) {
     float r;
     asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(r) : "l"(p));

@@ -18,6 +18,21 @@ struct LayerEpi {
     const float* vbn;          // [n_slots, vbn_len]
 };
 
+// source of a streamed weight matrix for the GEMV kernels: the noise slab (per-slot element offset) or the theta
+// matrix (per-slot parent row)
+struct GemvSrc {
+    const float* base;        // noise slab, or theta matrix
+    const int64_t* idx64;     // per-slot element offset (noise index) ...
+    const int32_t* idx32;     // ... or per-slot row (theta_idx) times `mul`
+    int64_t mul, off;         // off = layer weight offset inside the flat vector
+};
+
+extern int g_dne_gemv_bulk;
+// TMA-bulk-copy pipelined variant of the noise GEMV (gemv_bulk.cu).  Returns DNE_ERR_UNSUP if the shape is not covered.
+int dne_launch_gemv_bulk(const SlotArgs& sa, const GemvSrc& src, int G, const float* X, int64_t x_slot_stride, int K,
+                         int N, int rows_per_chunk, int n_chunks, int n_slots, float* part, int sm_count,
+                         cudaStream_t st);
+
 struct DensePlan {
     bool decomposed;
     int n_split, k_per_split;     // theta GEMM split-K

@@ -240,12 +240,6 @@ dense_theta_gemm_kernel(const float* __restrict__ X, int M, int K, int N, const 
 // ---------------------------------------------------------------------------------------------------
 // The same kernel also streams the PARENT weights for GA slots (theta rows selected per slot): the "slab" is then
 // the theta matrix and the per-group element offset is theta_idx * P (GemvSrc).
-struct GemvSrc {
-    const float* base;        // noise slab, or theta matrix
-    const int64_t* idx64;     // per-slot element offset (noise index) ...
-    const int32_t* idx32;     // ... or per-slot row (theta_idx) times `mul`
-    int64_t mul, off;         // off = layer weight offset inside the flat vector
-};
 
 template <int G, int U>
 __global__ void __launch_bounds__(256)
@@ -289,8 +283,8 @@ dense_noise_gemv_kernel(SlotArgs sa, GemvSrc src, const float* __restrict__ X, i
     int r = rw;   // row index local to the chunk, this reader takes rows rw, rw+RW, ...
     for (; r + (U - 1) * RW < rows; r += U * RW) {
         float4 v[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) v[u] = ldg_stream_f4(S + (int64_t)(k_beg + r + u * RW) * N);
+        static_assert(U == 8, "batched load helper is written for 8 rows");
+        ldg_stream_f4x8(S + (int64_t)(k_beg + r) * N, (int64_t)RW * N, v);
 #pragma unroll
         for (int u = 0; u < U; ++u) {
 #pragma unroll
@@ -584,7 +578,9 @@ int dne_launch_dense_layer(const dne_ctx* ctx, const SlotArgs& sa, const dne_lay
     } else {
         GemvSrc ts{sa.theta, nullptr, sa.theta_idx, sa.P, L.off_w};
         dim3 grid(p.n_chunks, (n_slots + p.Gt - 1) / p.Gt);
-        if (p.Gt == 2)
+        if (g_dne_gemv_bulk && dne_launch_gemv_bulk(sa, ts, p.Gt, X, x_slot_stride, K, N, p.rows_per_chunk, p.n_chunks,
+                                                    n_slots, part_theta, ctx->sm_count, st) == 0) {
+        } else if (p.Gt == 2)
             dense_noise_gemv_kernel<2, 8><<<grid, threads, gemv_smem(2), st>>>(sa, ts, X, x_slot_stride, K, N,
                                                                               p.rows_per_chunk, part_theta);
         else
@@ -597,7 +593,9 @@ int dne_launch_dense_layer(const dne_ctx* ctx, const SlotArgs& sa, const dne_lay
         dim3 grid(p.n_chunks, groups);
         const bool prof = ctx->prof_on && ctx->ev_n < ctx->ev_cap;
         if (prof) cudaEventRecord(ctx->ev[2 * ctx->ev_n], st);
-        if (p.G == 2)
+        if (g_dne_gemv_bulk && dne_launch_gemv_bulk(sa, ns, p.G, X, x_slot_stride, K, N, p.rows_per_chunk, p.n_chunks,
+                                                    n_slots, part_noise, ctx->sm_count, st) == 0) {
+        } else if (p.G == 2)
             dense_noise_gemv_kernel<2, 8><<<grid, threads, gemv_smem(2), st>>>(sa, ns, X, x_slot_stride, K, N,
                                                                               p.rows_per_chunk, part_noise);
         else

@@ -1,0 +1,215 @@
+// gemv_bulk.cu -- the HBM-bound noise GEMV with a TMA bulk-copy (cp.async.bulk) shared-memory pipeline.
+//
+// Same math and partial layout as dense_noise_gemv_kernel (forward_kernels.cu):
+//     part[group][chunk][g][n] = sum_{k in chunk} x_g[k] * W[k][n],   W = slab[E0 + k*N + n], E0 arbitrary alignment
+// but the weight rows do not pass through registers on their way in: a producer warp streams the 16B-ALIGNED superset
+// of the chunk (contiguous RB-row blocks, one cp.async.bulk each) into a ring of shared-memory stages, completion
+// tracked by mbarriers (full / empty), and 8 consumer warps read the rows back with conflict-free LDS.128.  The bytes
+// in flight are STAGES x 16 KB per CTA regardless of register allocation (the plain-LDG kernel is limited by how many
+// loads ptxas keeps in flight: measured 64 % of HBM peak; Little's law wants > 44 KB per SM).
+// CTAs are persistent: a static round-robin over (group, chunk) work items, the ring runs across item boundaries.
+#include "common.cuh"
+#include "forward.cuh"
+#include "epilogue.cuh"
+#include "tc05.cuh"
+
+using namespace tc05;
+
+int g_dne_gemv_bulk = 1;
+
+constexpr int GB_CONSUMERS = 256;
+constexpr int GB_THREADS = GB_CONSUMERS + 32;      // + one producer warp
+constexpr int GB_STAGES = 6;
+constexpr int GB_STAGE_BYTES = 16384;
+constexpr int GB_RPR = 4;                         // rows per reader per stage: (16384/4N) / (256/(N/4)) = 4 for every N
+
+template <int G>
+__global__ void __launch_bounds__(GB_THREADS)
+gemv_bulk_kernel(SlotArgs sa, GemvSrc src, const float* __restrict__ X, int64_t x_slot_stride, int K, int N,
+                 int rows_per_chunk, int n_chunks, int n_groups, float* __restrict__ part) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
+    float* stage_base = reinterpret_cast<float*>(smem);
+    float* red = reinterpret_cast<float*>(smem + GB_STAGES * GB_STAGE_BYTES);        // [RW][G][N+4]
+    __shared__ uint64_t full_bar[GB_STAGES], empty_bar[GB_STAGES];
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int NQ = N >> 2;
+    const int RW = GB_CONSUMERS / NQ;                  // row readers per stage
+    const int RB = GB_STAGE_BYTES / (N * 4);           // rows per stage
+    const int n_items = n_groups * n_chunks;
+
+    if (tid == 0) {
+        for (int s = 0; s < GB_STAGES; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], GB_CONSUMERS / 32);
+        }
+        fence_mbar_init();
+    }
+    __syncthreads();
+
+    auto item_active = [&](int item) {
+        const int slot0 = (item / n_chunks) * G;
+        bool any = false;
+#pragma unroll
+        for (int g = 0; g < G; ++g) any = any || slot_active(sa, slot0 + g);
+        return any;
+    };
+    auto item_base = [&](int item, int& k_beg, int& rows, int& a) -> const float* {
+        const int group = item / n_chunks, chunk = item % n_chunks;
+        const int slot0 = group * G;
+        k_beg = chunk * rows_per_chunk;
+        rows = min(K, k_beg + rows_per_chunk) - k_beg;
+        const int64_t E0 = (src.idx64 ? src.idx64[slot0] : (src.idx32 ? (int64_t)src.idx32[slot0] * src.mul : 0)) + src.off;
+        a = (int)(E0 & 3);
+        return src.base + (E0 - a) + (int64_t)k_beg * N;       // 16B-aligned start of the chunk's aligned rows
+    };
+
+    if (warp == GB_CONSUMERS / 32) {
+        // ===================== producer warp (one elected lane) =====================
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+                if (!item_active(item)) continue;
+                int k_beg, rows, a;
+                const float* base = item_base(item, k_beg, rows, a);
+                for (int r0 = 0; r0 < rows; r0 += RB, ++it) {
+                    const int s = it % GB_STAGES;
+                    mbar_wait(&empty_bar[s], ((it / GB_STAGES) & 1) ^ 1);
+                    const uint32_t bytes = (uint32_t)min(RB, rows - r0) * N * 4;
+                    mbar_arrive_expect_tx(&full_bar[s], bytes);
+                    bulk_g2s(stage_base + (size_t)s * (GB_STAGE_BYTES / 4), base + (int64_t)r0 * N, bytes, &full_bar[s]);
+                }
+            }
+        }
+        return;
+    }
+
+    // ===================== consumer warps =====================
+    const int t = tid % NQ, rw = tid / NQ;
+    uint32_t it = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        if (!item_active(item)) continue;
+        const int group = item / n_chunks, chunk = item % n_chunks;
+        const int slot0 = group * G;
+        int k_beg, rows, a;
+        const float* base = item_base(item, k_beg, rows, a);
+        const float* xg[G];
+#pragma unroll
+        for (int g = 0; g < G; ++g) xg[g] = X + (int64_t)(slot0 + g) * x_slot_stride + k_beg;
+
+        float acc[G][4];
+#pragma unroll
+        for (int g = 0; g < G; ++g)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) acc[g][c] = 0.0f;
+
+        for (int r0 = 0; r0 < rows; r0 += RB, ++it) {
+            const int s = it % GB_STAGES;
+            const int nr = min(RB, rows - r0);
+            // this reader's x values for the block (uniform per warp -> broadcast loads, L1 resident)
+            float xv[G][GB_RPR];
+#pragma unroll
+            for (int j = 0; j < GB_RPR; ++j) {
+                const int r = r0 + rw + j * RW;
+#pragma unroll
+                for (int g = 0; g < G; ++g) xv[g][j] = (j * RW + rw < nr) ? __ldg(xg[g] + r) : 0.0f;
+            }
+            mbar_wait(&full_bar[s], (it / GB_STAGES) & 1);
+            const float4* rows4 = reinterpret_cast<const float4*>(stage_base + (size_t)s * (GB_STAGE_BYTES / 4)) + t;
+#pragma unroll
+            for (int j = 0; j < GB_RPR; ++j) {
+                const int rl = rw + j * RW;                      // row inside the stage
+                if (rl < nr) {
+                    const float4 v = rows4[(size_t)rl * NQ];
+#pragma unroll
+                    for (int g = 0; g < G; ++g) {
+                        acc[g][0] = fmaf(xv[g][j], v.x, acc[g][0]);
+                        acc[g][1] = fmaf(xv[g][j], v.y, acc[g][1]);
+                        acc[g][2] = fmaf(xv[g][j], v.z, acc[g][2]);
+                        acc[g][3] = fmaf(xv[g][j], v.w, acc[g][3]);
+                    }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty_bar[s]);           // this warp is done reading stage s
+        }
+        // wrapped columns (q < a) of column quad 0: weight (k = r-1, n = N+q-a) sits in aligned row r = k+1
+        float wrap[G][4];
+#pragma unroll
+        for (int g = 0; g < G; ++g)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) wrap[g][c] = 0.0f;
+        if (t == 0 && a != 0) {
+            for (int rr = rw; rr < rows; rr += RW) {
+                const float4 v = ldg_stream_f4(base + (int64_t)(rr + 1) * N);
+#pragma unroll
+                for (int g = 0; g < G; ++g) {
+                    const float x = __ldg(xg[g] + rr);
+                    wrap[g][0] = fmaf(x, v.x, wrap[g][0]);
+                    wrap[g][1] = fmaf(x, v.y, wrap[g][1]);
+                    wrap[g][2] = fmaf(x, v.z, wrap[g][2]);
+                    wrap[g][3] = fmaf(x, v.w, wrap[g][3]);
+                }
+            }
+        }
+        // cross-reader reduction in fixed order, then this item's partial [G][N]
+        const int red_ld = N + 4;
+#pragma unroll
+        for (int g = 0; g < G; ++g) {
+            float* row = red + (rw * G + g) * red_ld;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                const int q = 4 * t + c;
+                if (q >= a) row[q - a] = acc[g][c];
+            }
+            if (t == 0) {
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+                    if (c < a) row[N + c - a] = wrap[g][c];
+            }
+        }
+        named_bar_sync(1, GB_CONSUMERS);
+        float* out = part + ((int64_t)group * n_chunks + chunk) * G * N;
+        for (int i = tid; i < G * N; i += GB_CONSUMERS) {
+            const int g = i / N, n = i % N;
+            float sum = 0.0f;
+            for (int w = 0; w < RW; ++w) sum += red[(w * G + g) * red_ld + n];
+            out[i] = sum;
+        }
+        named_bar_sync(1, GB_CONSUMERS);                         // red[] is reused by the next item
+    }
+}
+
+int dne_launch_gemv_bulk(const SlotArgs& sa, const GemvSrc& src, int G, const float* X, int64_t x_slot_stride, int K,
+                         int N, int rows_per_chunk, int n_chunks, int n_slots, float* part, int sm_count,
+                         cudaStream_t st) {
+    // shape cover: 4 | N, N/4 divides 256, a stage holds >= 1 row and at most 8 rows per reader
+    if (N % 4 != 0 || N * 4 > GB_STAGE_BYTES || (GB_CONSUMERS % (N / 4)) != 0) return DNE_ERR_UNSUP;
+    const int RW = GB_CONSUMERS / (N / 4), RB = GB_STAGE_BYTES / (N * 4);
+    if (RB != GB_RPR * RW || GB_STAGE_BYTES % (N * 4) != 0) return DNE_ERR_UNSUP;
+    const int n_groups = (n_slots + G - 1) / G;
+    const size_t smem = (size_t)GB_STAGES * GB_STAGE_BYTES + (size_t)RW * G * (N + 4) * sizeof(float) + 128;
+    const int n_items = n_groups * n_chunks;
+    int grid = 2 * sm_count;
+    if (grid > n_items) grid = n_items;
+    static bool attr_done[3] = {false, false, false};
+    if (G == 2) {
+        if (!attr_done[2]) {
+            if (cudaFuncSetAttribute(gemv_bulk_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024) != cudaSuccess)
+                return DNE_ERR_CUDA;
+            attr_done[2] = true;
+        }
+        gemv_bulk_kernel<2><<<grid, GB_THREADS, smem, st>>>(sa, src, X, x_slot_stride, K, N, rows_per_chunk, n_chunks,
+                                                           n_groups, part);
+    } else {
+        if (!attr_done[1]) {
+            if (cudaFuncSetAttribute(gemv_bulk_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024) != cudaSuccess)
+                return DNE_ERR_CUDA;
+            attr_done[1] = true;
+        }
+        gemv_bulk_kernel<1><<<grid, GB_THREADS, smem, st>>>(sa, src, X, x_slot_stride, K, N, rows_per_chunk, n_chunks,
+                                                           n_groups, part);
+    }
+    return 0;
+}

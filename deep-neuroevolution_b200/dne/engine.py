@@ -75,13 +75,13 @@ class SlotForward:
         if net.ob_kind == F.OB_ATARI_U8:
             F.check(L.dne_perturb_forward_conv(
                 self.ctx.handle, C.byref(net.desc), F.ptr(theta, torch.float32), F.ptr(self.noise_idx),
-                F.ptr(self.scale), F.ptr(self.theta_idx), F.ptr(self.active), n, int(bool(paired)),
+                F.ptr(self.scale), F.ptr(self.theta_idx), F.ptr(self.active), n, int(paired),
                 F.ptr(obs, torch.uint8), F.ptr(self.vbn), F.ptr(self.actions), F.ptr(self.logits),
                 F.ptr(self.ws), self.ws.numel(), F.stream_ptr()))
             return self.actions
         F.check(L.dne_perturb_forward_mlp(
             self.ctx.handle, C.byref(net.desc), F.ptr(theta, torch.float32), F.ptr(self.noise_idx),
-            F.ptr(self.scale), F.ptr(self.theta_idx), F.ptr(self.active), n, int(bool(paired)),
+            F.ptr(self.scale), F.ptr(self.theta_idx), F.ptr(self.active), n, int(paired),
             F.ptr(obs, torch.float32), F.ptr(ob_mean), F.ptr(ob_std), F.ptr(self.logits),
             F.ptr(self.ws), self.ws.numel(), F.stream_ptr()))
         return self.logits

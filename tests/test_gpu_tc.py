@@ -48,7 +48,9 @@ def test_tcgen05_gemm_selftest(n, k):
     ref = A.astype(np.float64) @ B.astype(np.float64).T
     scale = np.abs(ref).max()
     err = np.abs(got - ref).max()
-    assert err <= 2e-6 * scale, (err, scale)        # plain TF32 would be ~1e-3
+    # plain TF32 would be ~1e-3 * scale; 3xTF32 leaves the tensor core's own fp32 accumulation error (not IEEE
+    # round-to-nearest; measured 2e-6 * scale at K = 256), an order of magnitude inside the forward tolerance
+    assert err <= 1e-5 * scale, (err, scale)
 
 
 def _forward(ctx, net, theta, idx, scale, obs, paired, conv_tc, theta_idx=None):
