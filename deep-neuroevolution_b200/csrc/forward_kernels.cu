@@ -508,8 +508,8 @@ int dne_launch_conv_layer_simt(const SlotArgs& sa, const dne_layer_desc& L, cons
 
 // ---- dense-layer planning (shared by the ws query and the launcher) -----------------------------------
 static int pick_rows_per_chunk(int K, int N) {
-    // target ~256 KB of noise per CTA, but keep >= 1 and prefer exact divisors of K
-    int target = (int)((256 * 1024) / ((size_t)N * 4));
+    // target ~512 KB of noise per work item (persistent bulk-copy GEMV), prefer exact divisors of K
+    int target = (int)((512 * 1024) / ((size_t)N * 4));
     if (target < 8) target = 8;
     if (target >= K) return K;
     for (int r = target; r >= target / 2 && r >= 1; --r)

@@ -8,6 +8,10 @@
 // in flight are STAGES x 16 KB per CTA regardless of register allocation (the plain-LDG kernel is limited by how many
 // loads ptxas keeps in flight: measured 64 % of HBM peak; Little's law wants > 44 KB per SM).
 // CTAs are persistent: a static round-robin over (group, chunk) work items, the ring runs across item boundaries.
+//
+// Alignment trick (see forward_kernels.cu): thread t always owns aligned column quad q = 4t..4t+3.  Element (r, q) of
+// the aligned stream is weight (k = r, n = q - a) for q >= a and (k = r - 1, n = N + q - a) for q < a, a = E0 & 3.
+// Only quad 0 has the second kind; it keeps a second accumulator fed from the SAME staged rows with multiplier x[r-1].
 #include "common.cuh"
 #include "forward.cuh"
 #include "epilogue.cuh"
@@ -21,7 +25,8 @@ constexpr int GB_CONSUMERS = 256;
 constexpr int GB_THREADS = GB_CONSUMERS + 32;      // + one producer warp
 constexpr int GB_STAGES = 6;
 constexpr int GB_STAGE_BYTES = 16384;
-constexpr int GB_RPR = 4;                         // rows per reader per stage: (16384/4N) / (256/(N/4)) = 4 for every N
+constexpr int GB_RPR = 4;                          // rows per reader per stage: (16384/4N) / (256/(N/4)) = 4 for every N
+constexpr int GB_MAX_ROWS = 512;                   // rows per work item (x staging buffer)
 
 template <int G>
 __global__ void __launch_bounds__(GB_THREADS)
@@ -32,11 +37,12 @@ gemv_bulk_kernel(SlotArgs sa, GemvSrc src, const float* __restrict__ X, int64_t 
     float* stage_base = reinterpret_cast<float*>(smem);
     float* red = reinterpret_cast<float*>(smem + GB_STAGES * GB_STAGE_BYTES);        // [RW][G][N+4]
     __shared__ uint64_t full_bar[GB_STAGES], empty_bar[GB_STAGES];
+    __shared__ float xs[G][GB_MAX_ROWS + 8];           // xs[g][1 + r] = x_g[k_beg + r];  xs[g][0] = x_g[k_beg - 1]
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int NQ = N >> 2;
     const int RW = GB_CONSUMERS / NQ;                  // row readers per stage
-    const int RB = GB_STAGE_BYTES / (N * 4);           // rows per stage
+    const int RB = GB_RPR * RW;                        // rows per stage
     const int n_items = n_groups * n_chunks;
 
     if (tid == 0) {
@@ -87,6 +93,7 @@ gemv_bulk_kernel(SlotArgs sa, GemvSrc src, const float* __restrict__ X, int64_t 
 
     // ===================== consumer warps =====================
     const int t = tid % NQ, rw = tid / NQ;
+    const int red_ld = N + 4;
     uint32_t it = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
         if (!item_active(item)) continue;
@@ -94,67 +101,97 @@ gemv_bulk_kernel(SlotArgs sa, GemvSrc src, const float* __restrict__ X, int64_t 
         const int slot0 = group * G;
         int k_beg, rows, a;
         const float* base = item_base(item, k_beg, rows, a);
-        const float* xg[G];
-#pragma unroll
-        for (int g = 0; g < G; ++g) xg[g] = X + (int64_t)(slot0 + g) * x_slot_stride + k_beg;
 
-        float acc[G][4];
+        // stage x_g[k_beg-1 .. k_beg+rows) (the previous item's readers are past their last xs read: barrier C below)
+        for (int i = tid; i < G * (rows + 1); i += GB_CONSUMERS) {
+            const int g = i / (rows + 1), r = i % (rows + 1);
+            const int k = k_beg - 1 + r;
+            xs[g][r] = (k >= 0) ? X[(int64_t)(slot0 + g) * x_slot_stride + k] : 0.0f;
+        }
+        named_bar_sync(1, GB_CONSUMERS);                                   // barrier A
+
+        float acc[G][4], wrap[G][4];
 #pragma unroll
         for (int g = 0; g < G; ++g)
 #pragma unroll
-            for (int c = 0; c < 4; ++c) acc[g][c] = 0.0f;
+            for (int c = 0; c < 4; ++c) acc[g][c] = wrap[g][c] = 0.0f;
+        const bool do_wrap = (t == 0) && (a != 0);
 
         for (int r0 = 0; r0 < rows; r0 += RB, ++it) {
             const int s = it % GB_STAGES;
             const int nr = min(RB, rows - r0);
-            // this reader's x values for the block (uniform per warp -> broadcast loads, L1 resident)
-            float xv[G][GB_RPR];
+            const int rl0 = rw * GB_RPR;                 // this reader's first row inside the stage (contiguous rows)
+            // x multipliers: xm[g][j] = x[r0+rl0+j] (row itself), xm[g][-1 -> index 0] = x[r0+rl0-1] (wrap of the first row)
+            float xm[G][GB_RPR + 1];
 #pragma unroll
-            for (int j = 0; j < GB_RPR; ++j) {
-                const int r = r0 + rw + j * RW;
+            for (int g = 0; g < G; ++g)
 #pragma unroll
-                for (int g = 0; g < G; ++g) xv[g][j] = (j * RW + rw < nr) ? __ldg(xg[g] + r) : 0.0f;
-            }
+                for (int j = 0; j <= GB_RPR; ++j) xm[g][j] = xs[g][r0 + rl0 + j];        // xs index = 1 + (row - 1)
             mbar_wait(&full_bar[s], (it / GB_STAGES) & 1);
-            const float4* rows4 = reinterpret_cast<const float4*>(stage_base + (size_t)s * (GB_STAGE_BYTES / 4)) + t;
+            const float4* rows4 = reinterpret_cast<const float4*>(stage_base + (size_t)s * (GB_STAGE_BYTES / 4)) +
+                                  (size_t)rl0 * NQ + t;
+            if (nr == RB) {
+                float4 v[GB_RPR];
 #pragma unroll
-            for (int j = 0; j < GB_RPR; ++j) {
-                const int rl = rw + j * RW;                      // row inside the stage
-                if (rl < nr) {
-                    const float4 v = rows4[(size_t)rl * NQ];
+                for (int j = 0; j < GB_RPR; ++j) v[j] = rows4[(size_t)j * NQ];
+#pragma unroll
+                for (int j = 0; j < GB_RPR; ++j)
 #pragma unroll
                     for (int g = 0; g < G; ++g) {
-                        acc[g][0] = fmaf(xv[g][j], v.x, acc[g][0]);
-                        acc[g][1] = fmaf(xv[g][j], v.y, acc[g][1]);
-                        acc[g][2] = fmaf(xv[g][j], v.z, acc[g][2]);
-                        acc[g][3] = fmaf(xv[g][j], v.w, acc[g][3]);
+                        acc[g][0] = fmaf(xm[g][j + 1], v[j].x, acc[g][0]);
+                        acc[g][1] = fmaf(xm[g][j + 1], v[j].y, acc[g][1]);
+                        acc[g][2] = fmaf(xm[g][j + 1], v[j].z, acc[g][2]);
+                        acc[g][3] = fmaf(xm[g][j + 1], v[j].w, acc[g][3]);
+                    }
+                if (do_wrap) {
+#pragma unroll
+                    for (int j = 0; j < GB_RPR; ++j)
+#pragma unroll
+                        for (int g = 0; g < G; ++g) {     // aligned row r carries weight row r-1 in its columns q < a
+                            const float xp = (r0 + rl0 + j >= 1) ? xm[g][j] : 0.0f;
+                            wrap[g][0] = fmaf(xp, v[j].x, wrap[g][0]);
+                            wrap[g][1] = fmaf(xp, v[j].y, wrap[g][1]);
+                            wrap[g][2] = fmaf(xp, v[j].z, wrap[g][2]);
+                            wrap[g][3] = fmaf(xp, v[j].w, wrap[g][3]);
+                        }
+                }
+            } else {
+                for (int j = 0; j < GB_RPR; ++j) {
+                    if (rl0 + j < nr) {
+                        const float4 v = rows4[(size_t)j * NQ];
+#pragma unroll
+                        for (int g = 0; g < G; ++g) {
+                            acc[g][0] = fmaf(xm[g][j + 1], v.x, acc[g][0]);
+                            acc[g][1] = fmaf(xm[g][j + 1], v.y, acc[g][1]);
+                            acc[g][2] = fmaf(xm[g][j + 1], v.z, acc[g][2]);
+                            acc[g][3] = fmaf(xm[g][j + 1], v.w, acc[g][3]);
+                            if (do_wrap && (r0 + rl0 + j >= 1)) {
+                                wrap[g][0] = fmaf(xm[g][j], v.x, wrap[g][0]);
+                                wrap[g][1] = fmaf(xm[g][j], v.y, wrap[g][1]);
+                                wrap[g][2] = fmaf(xm[g][j], v.z, wrap[g][2]);
+                                wrap[g][3] = fmaf(xm[g][j], v.w, wrap[g][3]);
+                            }
+                        }
                     }
                 }
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty_bar[s]);           // this warp is done reading stage s
         }
-        // wrapped columns (q < a) of column quad 0: weight (k = r-1, n = N+q-a) sits in aligned row r = k+1
-        float wrap[G][4];
+        // the chunk's last weight row (k = rows-1) wraps into aligned row `rows`, the first row of the NEXT chunk:
+        // one 16-byte load per item
+        if (do_wrap && rw == 0) {
+            const float4 v = ldg_stream_f4(base + (int64_t)rows * N);
 #pragma unroll
-        for (int g = 0; g < G; ++g)
-#pragma unroll
-            for (int c = 0; c < 4; ++c) wrap[g][c] = 0.0f;
-        if (t == 0 && a != 0) {
-            for (int rr = rw; rr < rows; rr += RW) {
-                const float4 v = ldg_stream_f4(base + (int64_t)(rr + 1) * N);
-#pragma unroll
-                for (int g = 0; g < G; ++g) {
-                    const float x = __ldg(xg[g] + rr);
-                    wrap[g][0] = fmaf(x, v.x, wrap[g][0]);
-                    wrap[g][1] = fmaf(x, v.y, wrap[g][1]);
-                    wrap[g][2] = fmaf(x, v.z, wrap[g][2]);
-                    wrap[g][3] = fmaf(x, v.w, wrap[g][3]);
-                }
+            for (int g = 0; g < G; ++g) {
+                const float x = xs[g][rows];                      // x[k_beg + rows - 1]
+                wrap[g][0] = fmaf(x, v.x, wrap[g][0]);
+                wrap[g][1] = fmaf(x, v.y, wrap[g][1]);
+                wrap[g][2] = fmaf(x, v.z, wrap[g][2]);
+                wrap[g][3] = fmaf(x, v.w, wrap[g][3]);
             }
         }
         // cross-reader reduction in fixed order, then this item's partial [G][N]
-        const int red_ld = N + 4;
 #pragma unroll
         for (int g = 0; g < G; ++g) {
             float* row = red + (rw * G + g) * red_ld;
@@ -169,7 +206,7 @@ gemv_bulk_kernel(SlotArgs sa, GemvSrc src, const float* __restrict__ X, int64_t 
                     if (c < a) row[N + c - a] = wrap[g][c];
             }
         }
-        named_bar_sync(1, GB_CONSUMERS);
+        named_bar_sync(1, GB_CONSUMERS);                                   // barrier B
         float* out = part + ((int64_t)group * n_chunks + chunk) * G * N;
         for (int i = tid; i < G * N; i += GB_CONSUMERS) {
             const int g = i / N, n = i % N;
@@ -177,17 +214,17 @@ gemv_bulk_kernel(SlotArgs sa, GemvSrc src, const float* __restrict__ X, int64_t 
             for (int w = 0; w < RW; ++w) sum += red[(w * G + g) * red_ld + n];
             out[i] = sum;
         }
-        named_bar_sync(1, GB_CONSUMERS);                         // red[] is reused by the next item
+        named_bar_sync(1, GB_CONSUMERS);                                   // barrier C: red[] and xs[] reusable
     }
 }
 
 int dne_launch_gemv_bulk(const SlotArgs& sa, const GemvSrc& src, int G, const float* X, int64_t x_slot_stride, int K,
                          int N, int rows_per_chunk, int n_chunks, int n_slots, float* part, int sm_count,
                          cudaStream_t st) {
-    // shape cover: 4 | N, N/4 divides 256, a stage holds >= 1 row and at most 8 rows per reader
+    // shape cover: 4 | N, N/4 divides 256, one stage = GB_RPR rows per reader
     if (N % 4 != 0 || N * 4 > GB_STAGE_BYTES || (GB_CONSUMERS % (N / 4)) != 0) return DNE_ERR_UNSUP;
-    const int RW = GB_CONSUMERS / (N / 4), RB = GB_STAGE_BYTES / (N * 4);
-    if (RB != GB_RPR * RW || GB_STAGE_BYTES % (N * 4) != 0) return DNE_ERR_UNSUP;
+    const int RW = GB_CONSUMERS / (N / 4);
+    if (GB_RPR * RW * N * 4 != GB_STAGE_BYTES || rows_per_chunk > GB_MAX_ROWS) return DNE_ERR_UNSUP;
     const int n_groups = (n_slots + G - 1) / G;
     const size_t smem = (size_t)GB_STAGES * GB_STAGE_BYTES + (size_t)RW * G * (N + 4) * sizeof(float) + 128;
     const int n_items = n_groups * n_chunks;
@@ -196,7 +233,7 @@ int dne_launch_gemv_bulk(const SlotArgs& sa, const GemvSrc& src, int G, const fl
     static bool attr_done[3] = {false, false, false};
     if (G == 2) {
         if (!attr_done[2]) {
-            if (cudaFuncSetAttribute(gemv_bulk_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024) != cudaSuccess)
+            if (cudaFuncSetAttribute(gemv_bulk_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 108 * 1024) != cudaSuccess)
                 return DNE_ERR_CUDA;
             attr_done[2] = true;
         }
@@ -204,7 +241,7 @@ int dne_launch_gemv_bulk(const SlotArgs& sa, const GemvSrc& src, int G, const fl
                                                            n_groups, part);
     } else {
         if (!attr_done[1]) {
-            if (cudaFuncSetAttribute(gemv_bulk_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024) != cudaSuccess)
+            if (cudaFuncSetAttribute(gemv_bulk_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 108 * 1024) != cudaSuccess)
                 return DNE_ERR_CUDA;
             attr_done[1] = true;
         }
