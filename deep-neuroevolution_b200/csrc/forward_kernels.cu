@@ -572,9 +572,13 @@ int dne_launch_dense_layer(const dne_ctx* ctx, const SlotArgs& sa, const dne_lay
         return sm1 > sm2 ? sm1 : sm2;
     };
     if (p.Gt == 0) {
-        dim3 grid((N + DG_BN - 1) / DG_BN, (n_slots + DG_BM - 1) / DG_BM, p.n_split);
-        dense_theta_gemm_kernel<<<grid, DG_THREADS, 0, st>>>(X, n_slots, K, N, sa.theta + L.off_w, p.k_per_split,
-                                                            part_theta);
+        // tensor cores (tcgen05, 3xTF32) when enabled, fp32 SIMT otherwise
+        if (!(g_dne_conv_tc && dne_launch_theta_gemm_tc(X, n_slots, K, N, sa.theta + L.off_w, p.k_per_split, p.n_split,
+                                                        part_theta, st) == 0)) {
+            dim3 grid((N + DG_BN - 1) / DG_BN, (n_slots + DG_BM - 1) / DG_BM, p.n_split);
+            dense_theta_gemm_kernel<<<grid, DG_THREADS, 0, st>>>(X, n_slots, K, N, sa.theta + L.off_w, p.k_per_split,
+                                                                part_theta);
+        }
     } else {
         GemvSrc ts{sa.theta, nullptr, sa.theta_idx, sa.P, L.off_w};
         dim3 grid(p.n_chunks, (n_slots + p.Gt - 1) / p.Gt);

@@ -108,6 +108,15 @@ __device__ __forceinline__ void split_tf32(float x, float& hi, float& lo) {
     lo = __uint_as_float(l);
 }
 
+// Cheap variant used by the staging loops (4 integer/float ops instead of two cvt.rna sequences):
+// hi = x rounded to TF32 by adding half an ulp to the magnitude bits and masking, lo = (x - hi) truncated to TF32.
+// |lo| <= 2^-11 |x| and its truncation loses <= 2^-11 of it, so the dropped part is <= 2^-22 |x| per operand.
+__device__ __forceinline__ void split_tf32_fast(float x, float& hi, float& lo) {
+    const uint32_t hb = (__float_as_uint(x) + 0x1000u) & 0xFFFFE000u;
+    hi = __uint_as_float(hb);
+    lo = __uint_as_float(__float_as_uint(x - hi) & 0xFFFFE000u);
+}
+
 }  // namespace tc05
 
 // ---- 1-D bulk async copy (TMA engine, no tensor map): global -> shared, completion on an mbarrier ---------------

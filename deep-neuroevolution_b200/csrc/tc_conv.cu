@@ -91,6 +91,54 @@ conv_tc_kernel(SlotArgs sa, int64_t off_w, LayerEpi epi, const void* __restrict_
 
     constexpr uint32_t IDESC = idesc_tf32(128, COUT);
 
+    // uint8 observations: value/255 and its hi/lo TF32 split come from a 256-entry table (no IEEE division per pixel)
+    __shared__ float2 u8_lut[IN_U8 ? 256 : 1];
+    if (IN_U8) {
+        if (tid < 256) {
+            const float v = __fdiv_rn((float)tid, 255.0f);        // atari_wrappers.py:186
+            float hi, lo;
+            split_tf32_fast(v, hi, lo);
+            u8_lut[tid] = make_float2(hi, lo);
+        }
+        __syncthreads();
+    }
+
+    // Software pipeline: the raw global loads of chunk c+1 are issued (into registers) while chunk c is converted,
+    // stored, fenced and handed to the tensor core, so their latency overlaps the barrier and the MMA issue.
+    uint32_t rawA_u8[IN_U8 ? A_PER_THREAD : 1];
+    float4 rawA_f[IN_U8 ? 1 : A_PER_THREAD];
+    float rawB_t[B_PER_THREAD][4], rawB_n[B_PER_THREAD][4];
+    auto load_chunk = [&](int c) {
+        const int k0 = c * KC;
+#pragma unroll
+        for (int i = 0; i < A_PER_THREAD; ++i) {
+            const int u = tid + i * TC_THREADS;
+            const int q = u / Cfg::ROWS;
+            const int k = k0 + 4 * q;
+            const int ci = k % CIN, t = k / CIN;
+            const int kx = t % KS, ky = t / KS;
+            const int iy = a_iy0[i] + ky, ix = a_ix0[i] + kx;
+            const bool ok = a_ok[i] && iy >= 0 && iy < HIN && ix >= 0 && ix < HIN;
+            const int e = (iy * HIN + ix) * CIN + ci;
+            if (IN_U8) rawA_u8[IN_U8 ? i : 0] = ok ? *reinterpret_cast<const uint32_t*>(in_u8 + e) : 0u;
+            else rawA_f[IN_U8 ? 0 : i] = ok ? *reinterpret_cast<const float4*>(in_f + e) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int i = 0; i < B_PER_THREAD; ++i) {
+            const int u = tid + i * TC_THREADS;
+            if (u < B_UNITS) {
+                const int n = u % COUT, q = u / COUT;
+                const int64_t f = (int64_t)(k0 + 4 * q) * COUT + n;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    rawB_t[i][j] = tw[f + j * COUT];
+                    rawB_n[i][j] = nz[f + j * COUT];
+                }
+            }
+        }
+    };
+    load_chunk(0);
+
     for (int c = 0; c < Cfg::NCHUNK; ++c) {
         const int st = c & 1;
         if (c >= 2) mbar_wait(&bars[st], ((c >> 1) - 1) & 1);     // MMAs of chunk c-2 finished reading this stage
@@ -98,34 +146,25 @@ conv_tc_kernel(SlotArgs sa, int64_t off_w, LayerEpi epi, const void* __restrict_
         uint8_t* sA_lo = sA_hi + Cfg::A_BYTES;
         uint8_t* sB_hi = sA_lo + Cfg::A_BYTES;
         uint8_t* sB_lo = sB_hi + Cfg::B_BYTES;
-        const int k0 = c * KC;
-        // ---- stage A: im2col gather + hi/lo split ----
+        // ---- stage A: hi/lo split of the im2col values loaded one iteration ago ----
 #pragma unroll
         for (int i = 0; i < A_PER_THREAD; ++i) {
             const int u = tid + i * TC_THREADS;
             const int r = u % Cfg::ROWS, q = u / Cfg::ROWS;
-            const int k = k0 + 4 * q;
-            const int ci = k % CIN, t = k / CIN;
-            const int kx = t % KS, ky = t / KS;
-            const int iy = a_iy0[i] + ky, ix = a_ix0[i] + kx;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (a_ok[i] && iy >= 0 && iy < HIN && ix >= 0 && ix < HIN) {
-                const int e = (iy * HIN + ix) * CIN + ci;
-                if (IN_U8) {
-                    const uchar4 p = *reinterpret_cast<const uchar4*>(in_u8 + e);
-                    v.x = __fdiv_rn((float)p.x, 255.0f);
-                    v.y = __fdiv_rn((float)p.y, 255.0f);
-                    v.z = __fdiv_rn((float)p.z, 255.0f);
-                    v.w = __fdiv_rn((float)p.w, 255.0f);
-                } else {
-                    v = *reinterpret_cast<const float4*>(in_f + e);
-                }
-            }
             float4 hi, lo;
-            split_tf32(v.x, hi.x, lo.x);
-            split_tf32(v.y, hi.y, lo.y);
-            split_tf32(v.z, hi.z, lo.z);
-            split_tf32(v.w, hi.w, lo.w);
+            if (IN_U8) {
+                const uint32_t p = rawA_u8[IN_U8 ? i : 0];
+                const float2 e0 = u8_lut[p & 255u], e1 = u8_lut[(p >> 8) & 255u], e2 = u8_lut[(p >> 16) & 255u],
+                             e3 = u8_lut[IN_U8 ? (p >> 24) : 0];
+                hi = make_float4(e0.x, e1.x, e2.x, e3.x);
+                lo = make_float4(e0.y, e1.y, e2.y, e3.y);
+            } else {
+                const float4 v = rawA_f[IN_U8 ? 0 : i];
+                split_tf32_fast(v.x, hi.x, lo.x);
+                split_tf32_fast(v.y, hi.y, lo.y);
+                split_tf32_fast(v.z, hi.z, lo.z);
+                split_tf32_fast(v.w, hi.w, lo.w);
+            }
             *reinterpret_cast<float4*>(sA_hi + q * Cfg::A_PLANE + r * 16) = hi;
             *reinterpret_cast<float4*>(sA_lo + q * Cfg::A_PLANE + r * 16) = lo;
         }
@@ -135,21 +174,16 @@ conv_tc_kernel(SlotArgs sa, int64_t off_w, LayerEpi epi, const void* __restrict_
             const int u = tid + i * TC_THREADS;
             if (u < B_UNITS) {
                 const int n = u % COUT, q = u / COUT;
-                const int64_t f = (int64_t)(k0 + 4 * q) * COUT + n;
-                float4 w;
-                w.x = perturbed(tw[f], s, nz[f]);
-                w.y = perturbed(tw[f + COUT], s, nz[f + COUT]);
-                w.z = perturbed(tw[f + 2 * COUT], s, nz[f + 2 * COUT]);
-                w.w = perturbed(tw[f + 3 * COUT], s, nz[f + 3 * COUT]);
                 float4 hi, lo;
-                split_tf32(w.x, hi.x, lo.x);
-                split_tf32(w.y, hi.y, lo.y);
-                split_tf32(w.z, hi.z, lo.z);
-                split_tf32(w.w, hi.w, lo.w);
+                split_tf32_fast(perturbed(rawB_t[i][0], s, rawB_n[i][0]), hi.x, lo.x);
+                split_tf32_fast(perturbed(rawB_t[i][1], s, rawB_n[i][1]), hi.y, lo.y);
+                split_tf32_fast(perturbed(rawB_t[i][2], s, rawB_n[i][2]), hi.z, lo.z);
+                split_tf32_fast(perturbed(rawB_t[i][3], s, rawB_n[i][3]), hi.w, lo.w);
                 *reinterpret_cast<float4*>(sB_hi + q * Cfg::B_PLANE + n * 16) = hi;
                 *reinterpret_cast<float4*>(sB_lo + q * Cfg::B_PLANE + n * 16) = lo;
             }
         }
+        if (c + 1 < Cfg::NCHUNK) load_chunk(c + 1);               // in flight across the fence / barrier / MMA issue
         fence_proxy_async_smem();          // generic-proxy writes -> async proxy (tensor core reads)
         __syncthreads();
         if (tid == 0) {
@@ -340,4 +374,145 @@ extern "C" int dne_test_tc_gemm(const float* d_A, const float* d_B, float* d_C, 
     }
     DNE_LAUNCH_CHECK1();
     return DNE_OK;
+}
+
+// =====================================================================================================
+// Dense layer, shared-theta part on the tensor cores:  part[split][m][n] = sum_{k in split} X[m][k] * W[k][n]
+// (same contract as dense_theta_gemm_kernel).  CTA tile 128 x 128, k-chunks of 16, 3xTF32, operands staged by the
+// threads (A rows are K-contiguous float4 loads; B is transposed to [n][k] quads on the fly), two smem stages.
+// =====================================================================================================
+constexpr int TG_BM = 128, TG_BN = 128, TG_KC = 16;
+constexpr int TG_A_PLANE = TG_BM * 16, TG_B_PLANE = TG_BN * 16;
+constexpr int TG_A_BYTES = (TG_KC / 4) * TG_A_PLANE, TG_B_BYTES = (TG_KC / 4) * TG_B_PLANE;
+constexpr int TG_STAGE_BYTES = 2 * TG_A_BYTES + 2 * TG_B_BYTES;
+constexpr int TG_SMEM_BYTES = 2 * TG_STAGE_BYTES + 128;
+
+__global__ void __launch_bounds__(TC_THREADS)
+theta_gemm_tc_kernel(const float* __restrict__ X, int M, int K, int N, const float* __restrict__ W, int k_per_split,
+                     float* __restrict__ part) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
+    __shared__ uint64_t bars[2];
+    __shared__ uint32_t tmem_base_s;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int m0 = blockIdx.y * TG_BM, n0 = blockIdx.x * TG_BN, split = blockIdx.z;
+    const int kbeg = split * k_per_split, kend = min(K, kbeg + k_per_split);
+    const int nchunk = (kend - kbeg + TG_KC - 1) / TG_KC;
+
+    if (warp == 0) tmem_alloc(&tmem_base_s, 128);
+    if (tid == 32) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        fence_mbar_init();
+    }
+    fence_before_thread_sync();
+    __syncthreads();
+    fence_after_thread_sync();
+    const uint32_t tmem_base = tmem_base_s;
+    constexpr uint32_t IDESC = idesc_tf32(128, TG_BN);
+
+    // A: 128 rows x 4 k-quads = 512 units; B: 128 n x 4 k-quads = 512 units -> 2 + 2 units per thread
+    float4 rawA[2];
+    float rawB[2][4];
+    auto load_chunk = [&](int c) {
+        const int k0 = kbeg + c * TG_KC;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const int u = tid + i * TC_THREADS;
+            const int r = u % TG_BM, q = u / TG_BM;
+            const int m = m0 + r, k = k0 + 4 * q;
+            rawA[i] = (m < M && k < kend) ? *reinterpret_cast<const float4*>(X + (int64_t)m * K + k)
+                                          : make_float4(0.f, 0.f, 0.f, 0.f);
+            const int n = n0 + (u % TG_BN), kb = k0 + 4 * (u / TG_BN);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) rawB[i][j] = (n < N && kb + j < kend) ? W[(int64_t)(kb + j) * N + n] : 0.0f;
+        }
+    };
+    if (nchunk > 0) load_chunk(0);
+    for (int c = 0; c < nchunk; ++c) {
+        const int st = c & 1;
+        if (c >= 2) mbar_wait(&bars[st], ((c >> 1) - 1) & 1);
+        uint8_t* sA_hi = smem + st * TG_STAGE_BYTES;
+        uint8_t* sA_lo = sA_hi + TG_A_BYTES;
+        uint8_t* sB_hi = sA_lo + TG_A_BYTES;
+        uint8_t* sB_lo = sB_hi + TG_B_BYTES;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const int u = tid + i * TC_THREADS;
+            float4 hi, lo;
+            split_tf32_fast(rawA[i].x, hi.x, lo.x);
+            split_tf32_fast(rawA[i].y, hi.y, lo.y);
+            split_tf32_fast(rawA[i].z, hi.z, lo.z);
+            split_tf32_fast(rawA[i].w, hi.w, lo.w);
+            *reinterpret_cast<float4*>(sA_hi + (u / TG_BM) * TG_A_PLANE + (u % TG_BM) * 16) = hi;
+            *reinterpret_cast<float4*>(sA_lo + (u / TG_BM) * TG_A_PLANE + (u % TG_BM) * 16) = lo;
+            split_tf32_fast(rawB[i][0], hi.x, lo.x);
+            split_tf32_fast(rawB[i][1], hi.y, lo.y);
+            split_tf32_fast(rawB[i][2], hi.z, lo.z);
+            split_tf32_fast(rawB[i][3], hi.w, lo.w);
+            *reinterpret_cast<float4*>(sB_hi + (u / TG_BN) * TG_B_PLANE + (u % TG_BN) * 16) = hi;
+            *reinterpret_cast<float4*>(sB_lo + (u / TG_BN) * TG_B_PLANE + (u % TG_BN) * 16) = lo;
+        }
+        if (c + 1 < nchunk) load_chunk(c + 1);
+        fence_proxy_async_smem();
+        __syncthreads();
+        if (tid == 0) {
+            fence_after_thread_sync();
+            const uint32_t aH = smem_u32(sA_hi), aL = smem_u32(sA_lo), bH = smem_u32(sB_hi), bL = smem_u32(sB_lo);
+#pragma unroll
+            for (int k8 = 0; k8 < TG_KC / 8; ++k8) {
+                const uint64_t dAh = smem_desc(aH + 2 * k8 * TG_A_PLANE, TG_A_PLANE, 128);
+                const uint64_t dAl = smem_desc(aL + 2 * k8 * TG_A_PLANE, TG_A_PLANE, 128);
+                const uint64_t dBh = smem_desc(bH + 2 * k8 * TG_B_PLANE, TG_B_PLANE, 128);
+                const uint64_t dBl = smem_desc(bL + 2 * k8 * TG_B_PLANE, TG_B_PLANE, 128);
+                mma_tf32(tmem_base, dAh, dBh, IDESC, (c | k8) != 0);
+                mma_tf32(tmem_base, dAl, dBh, IDESC, 1);
+                mma_tf32(tmem_base, dAh, dBl, IDESC, 1);
+            }
+            mma_commit(&bars[st]);
+        }
+    }
+    if (nchunk > 0) mbar_wait(&bars[(nchunk - 1) & 1], ((nchunk - 1) >> 1) & 1);
+    fence_after_thread_sync();
+    float* P = part + (int64_t)split * M * N;
+    const int lg = warp & 3, ch = warp >> 2;
+    const int m = m0 + lg * 32 + lane;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int nc = ch * 64 + j * 16;
+        float v[16];
+        if (nchunk > 0) tmem_ld16(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)nc, v);
+        else {
+#pragma unroll
+            for (int x = 0; x < 16; ++x) v[x] = 0.0f;
+        }
+        if (m < M) {
+#pragma unroll
+            for (int x = 0; x < 16; x += 4) {
+                const int n = n0 + nc + x;
+                if (n + 3 < N) *reinterpret_cast<float4*>(P + (int64_t)m * N + n) = make_float4(v[x], v[x + 1], v[x + 2], v[x + 3]);
+                else
+                    for (int y = 0; y < 4; ++y)
+                        if (n + y < N) P[(int64_t)m * N + n + y] = v[x + y];
+            }
+        }
+    }
+    fence_before_thread_sync();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_base, 128);
+}
+
+// returns 0 on launch, DNE_ERR_UNSUP if the shape is not covered (caller falls back to the SIMT GEMM)
+int dne_launch_theta_gemm_tc(const float* X, int M, int K, int N, const float* W, int k_per_split, int n_split,
+                             float* part, cudaStream_t st) {
+    if (K % 4 != 0 || N % 4 != 0 || k_per_split % TG_KC != 0) return DNE_ERR_UNSUP;
+    static bool attr_done = false;
+    if (!attr_done) {
+        if (cudaFuncSetAttribute(theta_gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TG_SMEM_BYTES) != cudaSuccess)
+            return DNE_ERR_CUDA;
+        attr_done = true;
+    }
+    dim3 grid((N + TG_BN - 1) / TG_BN, (M + TG_BM - 1) / TG_BM, n_split);
+    theta_gemm_tc_kernel<<<grid, TC_THREADS, TG_SMEM_BYTES, st>>>(X, M, K, N, W, k_per_split, part);
+    return 0;
 }
