@@ -127,6 +127,8 @@ def run_b200(args):
     assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}"
     peaks, peak_src = load_peaks()
     L = F.lib()
+    if os.environ.get("DNE_GEMV_CTAS"):
+        F.check(L.dne_set_option(b"gemv_ctas_per_sm", int(os.environ["DNE_GEMV_CTAS"])))
 
     t0 = time.time()
     noise = SharedNoiseTable(count=args.noise_count, device=dev)
@@ -148,6 +150,10 @@ def run_b200(args):
     part = args.slots // NS
     sfs = [SlotForward(ctx, net, part) for _ in range(NS)]
     streams = [torch.cuda.Stream(device=dev) for _ in range(NS)]
+    PHASED = os.environ.get("DNE_BENCH_PHASED", "1") == "1"
+    phase_ev = [torch.cuda.Event() for _ in range(2)]
+    for e in phase_ev:
+        e.record()                                               # materialise the handles
     R = 4                                                        # observation pool blocks, rotated every tick
     pool = torch.randint(0, 256, (R, args.slots, 84, 84, 4), dtype=torch.uint8, device=dev)
     rew_pool = (torch.rand(64, args.slots, device=dev) < 0.05).float() * 10.0
@@ -185,6 +191,10 @@ def run_b200(args):
                     tally["launches"] += 1
                     tally["pairs"] += len(parts[h])
                     with torch.cuda.stream(streams[h]):
+                        if NS == 2 and PHASED:
+                            # table h waits for the OTHER table to reach its HBM-bound GEMV, then records its own
+                            F.check(L.dne_set_phase_events(ctx.handle, C.c_void_p(phase_ev[1 - h].cuda_event),
+                                                           C.c_void_p(phase_ev[h].cuda_event)))
                         sfs[h].forward(upd.theta, blk[h * part:(h + 1) * part], paired=True)
                         ret_acc[h * part:(h + 1) * part] += rew_pool[t % 64, h * part:(h + 1) * part]
             for s in streams:

@@ -21,6 +21,10 @@ struct dne_ctx {
     // optional CUDA-event timing of the dominant kernel (dense_noise_gemv) on the launching stream
     cudaEvent_t* ev;        // 2 * ev_cap events
     int ev_cap, ev_n, prof_on;
+    // optional phase events of the NEXT forward call (two half-tables on two streams, phase-shifted by half a tick)
+    void* ev_wait;          // the forward's stream waits for this event before its first kernel
+    void* ev_record;        // recorded right before the first HBM-bound noise GEMV of the call
+    int ev_record_done;
 };
 extern unsigned long long g_dne_launches;   // kernels launched by this library (process-wide)
 #define DNE_LAUNCHED(n) (g_dne_launches += (unsigned long long)(n))

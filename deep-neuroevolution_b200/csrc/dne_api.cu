@@ -42,6 +42,8 @@ extern "C" int dne_ctx_create(int device, dne_ctx** out) {
     c->scratch = nullptr;
     c->ev = nullptr;
     c->ev_cap = c->ev_n = c->prof_on = 0;
+    c->ev_wait = c->ev_record = nullptr;
+    c->ev_record_done = 0;
     cudaError_t e = cudaMalloc(&c->scratch, sizeof(double) * DNE_SCRATCH_DOUBLES);
     if (e != cudaSuccess) {
         delete c;
@@ -69,6 +71,7 @@ extern "C" int dne_set_option(const char* name, int value) {
     DNE_CHECK_ARG(name, "name is null");
     if (strcmp(name, "conv_tc") == 0) { g_dne_conv_tc = value ? 1 : 0; return DNE_OK; }
     if (strcmp(name, "gemv_bulk") == 0) { g_dne_gemv_bulk = value ? 1 : 0; return DNE_OK; }
+    if (strcmp(name, "gemv_ctas_per_sm") == 0 && value >= 1 && value <= 2) { g_dne_gemv_ctas_per_sm = value; return DNE_OK; }
     dne_set_error("dne_set_option: unknown option '%s'", name);
     return DNE_ERR_ARG;
 }
@@ -208,6 +211,10 @@ static int forward_impl(dne_ctx* ctx, const dne_net_desc* net, const float* d_th
     DNE_CHECK_ARG(!needs_vbn || d_vbn, "net has batch-norm layers: d_vbn (dne_vbn_reference_pass) required");
 
     cudaStream_t st = (cudaStream_t)stream;
+    // phase events (dne_set_phase_events): consumed by this call
+    if (ctx->ev_wait) DNE_CUDA(cudaStreamWaitEvent(st, (cudaEvent_t)ctx->ev_wait, 0));
+    ctx->ev_wait = nullptr;
+    ctx->ev_record_done = 0;
     char* ws = (char*)d_ws;
     SlotArgs sa;
     sa.theta = d_theta;
@@ -269,6 +276,20 @@ static int forward_impl(dne_ctx* ctx, const dne_net_desc* net, const float* d_th
         cur_elems = fp.act_elems[l];
         cur_u8 = false;
     }
+    if (ctx->ev_record && !ctx->ev_record_done) DNE_CUDA(cudaEventRecord((cudaEvent_t)ctx->ev_record, st));
+    ctx->ev_record = nullptr;
+    return DNE_OK;
+}
+
+// Phase-shifted double buffering of two slot tables on two streams: the NEXT forward call on `ctx` first makes its
+// stream wait for `wait_event` (nullable) and records `record_event` (nullable) right before its first HBM-bound noise
+// GEMV.  With table A recording eA / waiting eB and table B recording eB / waiting eA, the compute-bound conv phase
+// of one table runs under the HBM-bound GEMV of the other instead of both tables doing the same phase in lockstep.
+extern "C" int dne_set_phase_events(dne_ctx* ctx, void* wait_event, void* record_event) {
+    DNE_CHECK_ARG(ctx, "ctx is null");
+    ctx->ev_wait = wait_event;
+    ctx->ev_record = record_event;
+    ctx->ev_record_done = 0;
     return DNE_OK;
 }
 

@@ -28,6 +28,7 @@ struct GemvSrc {
 };
 
 extern int g_dne_gemv_bulk;
+extern int g_dne_gemv_ctas_per_sm;
 // TMA-bulk-copy pipelined variant of the noise GEMV (gemv_bulk.cu).  Returns DNE_ERR_UNSUP if the shape is not covered.
 int dne_launch_gemv_bulk(const SlotArgs& sa, const GemvSrc& src, int G, const float* X, int64_t x_slot_stride, int K,
                          int N, int rows_per_chunk, int n_chunks, int n_slots, float* part, int sm_count,

@@ -593,6 +593,10 @@ int dne_launch_dense_layer(const dne_ctx* ctx, const SlotArgs& sa, const dne_lay
     }
     {
         GemvSrc ns{sa.noise, sa.noise_idx, nullptr, 0, L.off_w};
+        if (ctx->ev_record && !ctx->ev_record_done) {          // phase event: the HBM-bound part of this call starts
+            cudaEventRecord((cudaEvent_t)ctx->ev_record, st);
+            const_cast<dne_ctx*>(ctx)->ev_record_done = 1;
+        }
         const int groups = (n_slots + p.G - 1) / p.G;
         dim3 grid(p.n_chunks, groups);
         const bool prof = ctx->prof_on && ctx->ev_n < ctx->ev_cap;

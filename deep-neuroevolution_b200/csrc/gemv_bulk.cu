@@ -20,6 +20,7 @@
 using namespace tc05;
 
 int g_dne_gemv_bulk = 1;
+int g_dne_gemv_ctas_per_sm = 2;
 
 constexpr int GB_CONSUMERS = 256;
 constexpr int GB_THREADS = GB_CONSUMERS + 32;      // + one producer warp
@@ -228,11 +229,12 @@ int dne_launch_gemv_bulk(const SlotArgs& sa, const GemvSrc& src, int G, const fl
     const int n_groups = (n_slots + G - 1) / G;
     const size_t smem = (size_t)GB_STAGES * GB_STAGE_BYTES + (size_t)RW * G * (N + 4) * sizeof(float) + 128;
     const int n_items = n_groups * n_chunks;
-    int grid = 2 * sm_count;
+    int grid = g_dne_gemv_ctas_per_sm * sm_count;   // 1 CTA/SM leaves room for the other stream's conv CTAs to co-reside
     if (grid > n_items) grid = n_items;
     static bool attr_done[3] = {false, false, false};
     if (G == 2) {
         if (!attr_done[2]) {
+            cudaFuncSetAttribute(gemv_bulk_kernel<2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
             if (cudaFuncSetAttribute(gemv_bulk_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 108 * 1024) != cudaSuccess)
                 return DNE_ERR_CUDA;
             attr_done[2] = true;
@@ -241,6 +243,7 @@ int dne_launch_gemv_bulk(const SlotArgs& sa, const GemvSrc& src, int G, const fl
                                                            n_groups, part);
     } else {
         if (!attr_done[1]) {
+            cudaFuncSetAttribute(gemv_bulk_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
             if (cudaFuncSetAttribute(gemv_bulk_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 108 * 1024) != cudaSuccess)
                 return DNE_ERR_CUDA;
             attr_done[1] = true;

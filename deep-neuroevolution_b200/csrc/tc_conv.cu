@@ -252,6 +252,7 @@ static int launch_conv_tc(const SlotArgs& sa, const dne_layer_desc& L, const Lay
     auto kern = conv_tc_kernel<CIN, COUT, KS, STRIDE, HIN, HOUT, PAD, IN_U8, MTC, KC>;
     static bool attr_done = false;
     if (!attr_done) {
+        cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES) != cudaSuccess)
             return DNE_ERR_CUDA;
         attr_done = true;
@@ -508,6 +509,7 @@ int dne_launch_theta_gemm_tc(const float* X, int M, int K, int N, const float* W
     if (K % 4 != 0 || N % 4 != 0 || k_per_split % TG_KC != 0) return DNE_ERR_UNSUP;
     static bool attr_done = false;
     if (!attr_done) {
+        cudaFuncSetAttribute(theta_gemm_tc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         if (cudaFuncSetAttribute(theta_gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TG_SMEM_BYTES) != cudaSuccess)
             return DNE_ERR_CUDA;
         attr_done = true;

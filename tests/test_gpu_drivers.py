@@ -1,0 +1,144 @@
+"""GPU tests of the reference-facing drivers (es_distributed.{es,ga,nses}.run_master) on BASELINE.json configs[0]-
+style plumbing runs: the reference's configuration dictionaries drive the engine, and every generation's bookkeeping
+and update is re-derived by the oracle from the same (noise indices, returns)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+if not torch.cuda.is_available():
+    pytest.skip("needs a CUDA device", allow_module_level=True)
+
+from oracle import oracle as O                 # noqa: E402
+from dne.envs import SyntheticAtariEnv          # noqa: E402
+from dne.noise import SharedNoiseTable          # noqa: E402
+
+NOISE_COUNT = 6_000_000
+FROSTBITE_ES = {      # configurations/frostbite_es.json (reference), population scaled down like BASELINE.json configs[0]
+    "config": {"calc_obstat_prob": 0.0, "episodes_per_batch": 16, "eval_prob": 0.1, "l2coeff": 0.005,
+               "noise_stdev": 0.005, "snapshot_freq": 0, "timesteps_per_batch": 10, "return_proc_mode": "centered_rank",
+               "episode_cutoff_mode": 5000},
+    "env_id": "FrostbiteNoFrameskip-v4",
+    "optimizer": {"args": {"stepsize": 0.01}, "type": "adam"},
+    "policy": {"args": {}, "type": "ESAtariPolicy"},
+}
+FROSTBITE_GA = {      # configurations/frostbite_ga.json
+    "config": {"calc_obstat_prob": 0.0, "episodes_per_batch": 12, "eval_prob": 0.0, "l2coeff": 0.005,
+               "noise_stdev": 0.005, "snapshot_freq": 0, "timesteps_per_batch": 10, "return_proc_mode": "centered_rank",
+               "episode_cutoff_mode": 5000},
+    "population_size": 4, "num_elites": 1, "env_id": "FrostbiteNoFrameskip-v4",
+    "policy": {"args": {"nonlin_type": "relu"}, "type": "GAAtariPolicy"},
+}
+FROSTBITE_NSR = {     # configurations/frostbite_nsres.json
+    "config": {"calc_obstat_prob": 0.0, "episodes_per_batch": 8, "eval_prob": 0.0, "l2coeff": 0.005, "noise_stdev": 0.02,
+               "snapshot_freq": 0, "timesteps_per_batch": 10, "return_proc_mode": "centered_sign_rank",
+               "episode_cutoff_mode": 5000},
+    "env_id": "FrostbiteNoFrameskip-v4", "algo_type": "nsr",
+    "novelty_search": {"k": 3, "population_size": 2, "num_rollouts": 1, "selection_method": "novelty_prob"},
+    "optimizer": {"args": {"stepsize": 0.01}, "type": "adam"},
+    "policy": {"args": {}, "type": "ESAtariPolicy"},
+}
+
+
+@pytest.fixture(scope="module")
+def host_noise():
+    return O.noise_table(NOISE_COUNT)
+
+
+@pytest.fixture(scope="module")
+def noise(host_noise):
+    return SharedNoiseTable(host_noise=host_noise, device="cuda:0")
+
+
+def test_reference_config_files_parse_unchanged():
+    """The reference's own configuration keys are the ones the drivers read (no renamed / extra required keys)."""
+    from es_distributed.es import Config
+    ref = {"config": {"calc_obstat_prob": 0.0, "episodes_per_batch": 5000, "eval_prob": 0.01, "l2coeff": 0.005,
+                      "noise_stdev": 0.005, "snapshot_freq": 20, "timesteps_per_batch": 10000,
+                      "return_proc_mode": "centered_rank", "episode_cutoff_mode": 5000}}
+    cfg = Config(**ref["config"])
+    assert cfg.episodes_per_batch == 5000 and cfg.episode_cutoff_mode == 5000
+
+
+def test_es_run_master_generation_matches_oracle(noise, host_noise, tmp_path):
+    from es_distributed import es as ES
+    env = SyntheticAtariEnv(8, episode_len=(3, 9), seed=3)
+    log = []
+    theta_before = {}
+
+    def on_it(it, stats, extra):
+        log.append((it, dict(stats), {k: (v.clone() if hasattr(v, "clone") else np.array(v)) for k, v in extra.items()
+                                      if k in ("noise_inds_n", "returns_n2", "lengths_n2", "g", "theta")}))
+    ES.set_default_noise(noise)
+    # capture theta0 by seeding the policy the same way run_master does
+    theta_final = ES.run_master({"unix_socket_path": None}, str(tmp_path), json.loads(json.dumps(FROSTBITE_ES)),
+                                max_iterations=2, n_slots=8, env=env, noise=noise, seed=11, on_iteration=on_it)
+    assert len(log) == 2 and theta_final.dtype == np.float32 and theta_final.shape == (1009058,)
+    net = O.make_net("ESAtariPolicy")
+    P = net.num_params
+    from es_distributed import policies
+    pol = policies.ESAtariPolicy(env.observation_space, env.action_space, seed=11)
+    theta = pol.get_trainable_flat()
+    adam = O.Adam(theta, 0.01)
+    for it, stats, ex in log:
+        idx, ret = ex["noise_inds_n"], ex["returns_n2"]
+        assert idx.dtype == np.int64 and ret.shape == (len(idx), 2) and ret.dtype == np.float32
+        assert len(idx) >= 8 and ex["lengths_n2"].min() >= 3 and ex["lengths_n2"].max() <= 9
+        assert (idx >= 0).all() and (idx <= NOISE_COUNT - P).all()
+        assert stats["EpisodesThisIter"] == ret.size and stats["TimestepsThisIter"] == int(ex["lengths_n2"].sum())
+        g, ratio, new_theta = O.es_generation_update(adam.theta, adam, host_noise, idx, ret, 0.005)
+        got_g = ex["g"].cpu().numpy()
+        assert np.abs(got_g - g).max() <= 1e-5 * np.abs(g).max()
+        np.testing.assert_allclose(ex["theta"].cpu().numpy(), new_theta, rtol=0, atol=2e-7)
+        assert stats["UpdateRatio"] == pytest.approx(float(ratio), rel=1e-4)
+    np.testing.assert_allclose(theta_final, adam.theta, rtol=0, atol=2e-7)
+    assert os.path.exists(os.path.join(str(tmp_path), "log.txt"))
+
+
+def test_ga_run_master_bookkeeping(noise, host_noise, tmp_path):
+    from es_distributed import ga as GA
+    env = SyntheticAtariEnv(8, episode_len=4, seed=5, num_actions=6)
+    log = []
+    GA.set_default_noise(noise)
+    pop, score = GA.run_master(None, str(tmp_path), json.loads(json.dumps(FROSTBITE_GA)), max_iterations=3, n_slots=8,
+                               env=env, noise=noise, seed=2,
+                               on_iteration=lambda it, st, ex: log.append((it, st, {k: (v.clone() if hasattr(v, "clone") else v)
+                                                                                    for k, v in ex.items()})))
+    assert len(pop) == 4 and len(score) == 4 and len(log) == 3
+    net = O.make_net("GAAtariPolicy", num_actions=6)
+    prev_pop, prev_score = [], np.array([], dtype=np.float32)
+    for it, st, ex in log:
+        genomes, returns = ex["genomes"], ex["returns"]
+        assert len(genomes) == 12 and all(len(g) == it for g in genomes)          # chains grow by one seed a generation
+        if it > 1:
+            assert all(tuple(g[:-1]) in [tuple(p) for p in prev_pop] for g in genomes)   # parent drawn from the population
+        cand = [tuple(p) for p in prev_pop[:1]] + [tuple(g) for g in genomes]        # ga.py:136-140 (elite first)
+        fit = np.concatenate([prev_score[:1], returns]).astype(np.float32)
+        sel = O.ga_truncate(fit, 4)
+        assert [tuple(p) for p in ex["population"]] == [cand[i] for i in sel]
+        np.testing.assert_array_equal(ex["population_score"], fit[sel])
+        assert ex["population_score"][0] == fit.max()                               # ga.py:149
+        elite = O.ga_materialize_cpu(net, host_noise, list(ex["population"][0]), 0.005)
+        np.testing.assert_allclose(ex["elite_theta"].cpu().numpy(), elite, rtol=1e-6, atol=1e-9)
+        prev_pop, prev_score = ex["population"], ex["population_score"]
+
+
+def test_nsr_run_master_novelty_and_update(noise, host_noise, tmp_path):
+    from es_distributed import nses as NS
+    env = SyntheticAtariEnv(8, episode_len=(3, 7), seed=9)
+    log = []
+    NS.set_default_noise(noise)
+    NS.run_master(None, str(tmp_path), json.loads(json.dumps(FROSTBITE_NSR)), max_iterations=2, n_slots=8, env=env,
+                  noise=noise, seed=4, on_iteration=lambda it, st, ex: log.append((it, st, dict(ex, g=ex["g"].clone()), len(ex["archive"]))))
+    assert len(log) == 2
+    for it, st, ex, arch_len in log:
+        assert arch_len == 2 + it                                                     # nses.py:113-114, 246-247
+        arch = ex["archive"].seqs[:arch_len - 1]                                     # archive as the rollouts saw it
+        nov = np.array([O.compute_novelty_vs_archive(arch, b, 3) for b in ex["bcs"]], dtype=np.float32).reshape(-1, 2)
+        np.testing.assert_allclose(ex["novelty_n2"], nov, rtol=1e-6)
+        proc = O.nsr_blend(ex["returns_n2"], nov)                                     # nses.py:221-228
+        g = O.es_gradient(proc, host_noise, ex["noise_inds_n"], 1009058)
+        assert np.abs(ex["g"].cpu().numpy() - g).max() <= 1e-5 * np.abs(g).max()
