@@ -11,6 +11,7 @@ Tolerances (stated once):
     actions must agree wherever the oracle's top-2 logit gap exceeds that bound.
 """
 import ctypes as C
+import zlib
 
 import numpy as np
 import pytest
@@ -168,8 +169,10 @@ def _theta_for(net_o, rs, scale=0.05):
 
 
 def _check_logits_actions(logits, actions, ref_logits, tol=2e-5):
-    bound = tol * max(1.0, float(np.abs(ref_logits).max()))
-    assert np.abs(logits - ref_logits).max() <= bound, (np.abs(logits - ref_logits).max(), bound)
+    """Per-row bound (a slot with a large perturbation scale has much larger logits than its neighbours)."""
+    bound = tol * np.maximum(1.0, np.abs(ref_logits).max(axis=1))
+    err = np.abs(logits - ref_logits).max(axis=1)
+    assert (err <= bound).all(), (err, bound)
     srt = np.sort(ref_logits, axis=1)
     decided = (srt[:, -1] - srt[:, -2]) > 2 * bound
     ref_act = np.argmax(ref_logits, axis=1)
@@ -183,7 +186,7 @@ def test_conv_policy_forward_vs_oracle(ctx, host_noise, name, A, paired):
     net = N.make_net(name, num_actions=A)
     net_o = O.make_net(name, num_actions=A)
     assert net.num_params == net_o.num_params
-    rs = np.random.RandomState(hash(name) % 1000)
+    rs = np.random.RandomState(zlib.crc32(name.encode()) % 1000)      # deterministic across processes
     P = net.num_params
     theta = _theta_for(net_o, rs)
     n_slots = 6
