@@ -44,7 +44,7 @@ def parse():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference", "cpu-sample"])
     ap.add_argument("--episode-len", type=int, default=int(os.environ.get("DNE_BENCH_T", 1000)))
     ap.add_argument("--pop", type=int, default=POP)
     ap.add_argument("--slots", type=int, default=SLOTS)
@@ -268,6 +268,8 @@ def run_b200(args):
     if not args.no_e2e:
         from es_distributed import es as ES
         from dne.envs import SyntheticAtariEnv
+        from es_distributed import tabular_logger
+        tabular_logger.set_quiet(True)          # stdout carries exactly one JSON line
         ES.set_default_noise(noise)
         ES._STATE["ctx"] = ctx
         env = SyntheticAtariEnv(args.slots, episode_len=T, seed=rank)
@@ -323,6 +325,20 @@ def run_b200(args):
 
 # ---------------------------------------------------------------------------------------------------------------
 def cpu_baseline(args, noise_host):
+    """Run the bounded CPU sample in a FRESH process (forking 100+ workers out of a process that holds a CUDA context
+    and pinned pools is slow and would distort the sample)."""
+    cmd = [sys.executable, os.path.abspath(__file__), "--impl", "cpu-sample", "--pop", str(args.pop),
+           "--episode-len", str(args.episode_len), "--cpu-sample-steps", str(args.cpu_sample_steps),
+           "--noise-count", str(args.noise_count)]
+    try:
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=300,
+                           env={k: v for k, v in os.environ.items() if k not in ("RANK", "WORLD_SIZE", "LOCAL_RANK")})
+        return json.loads(r.stdout.strip().splitlines()[-1])
+    except Exception as e:          # never lose the GPU numbers to a baseline hiccup
+        return {"value": None, "unit": "env-steps/s", "cores": None, "kind": "port", "sample": f"failed: {e!r}"}
+
+
+def cpu_sample(args, noise_host=None):
     """Reference worker loop + master update on the host cores, bounded sample (oracle/cpu_worker.py)."""
     from oracle import oracle as O
     from oracle import cpu_worker as W
@@ -402,7 +418,9 @@ def run_reference(args):
 
 if __name__ == "__main__":
     a = parse()
-    if a.impl == "reference":
+    if a.impl == "cpu-sample":
+        print(json.dumps(cpu_sample(a)))
+    elif a.impl == "reference":
         run_reference(a)
     else:
         run_b200(a)
