@@ -36,7 +36,7 @@ struct TcConvCfg {
 };
 
 template <int CIN, int COUT, int KS, int STRIDE, int HIN, int HOUT, int PAD, bool IN_U8, int MTC, int KC>
-__global__ void __launch_bounds__(TC_THREADS)
+__global__ void __launch_bounds__(TC_THREADS, 3)
 conv_tc_kernel(SlotArgs sa, int64_t off_w, LayerEpi epi, const void* __restrict__ in_base, int64_t in_slot_stride,
                int64_t in_img_stride, float* __restrict__ out_base, int64_t out_slot_stride, int64_t out_img_stride) {
     using Cfg = TcConvCfg<CIN, COUT, KS, STRIDE, HIN, HOUT, PAD, IN_U8, MTC, KC>;
@@ -90,6 +90,10 @@ conv_tc_kernel(SlotArgs sa, int64_t off_w, LayerEpi epi, const void* __restrict_
     constexpr int B_PER_THREAD = (B_UNITS + TC_THREADS - 1) / TC_THREADS;
 
     constexpr uint32_t IDESC = idesc_tf32(128, COUT);
+
+    // per-output-channel epilogue parameters (perturbed bias, virtual-BN statistics / scale / shift) built once per CTA
+    __shared__ ChanEpi epi_s[COUT];
+    if (tid < COUT) epi_s[tid] = make_chan_epi(sa, epi, slot, COUT, tid, th, idx, s);
 
     // uint8 observations: value/255 and its hi/lo TF32 split come from a 256-entry table (no IEEE division per pixel)
     __shared__ float2 u8_lut[IN_U8 ? 256 : 1];
@@ -221,9 +225,6 @@ conv_tc_kernel(SlotArgs sa, int64_t off_w, LayerEpi epi, const void* __restrict_
         if ((j & 1) != ch && COUT > 16) continue;                 // warps w and w+4 share lanes: split the column groups
         if (COUT == 16 && ch != 0) continue;
         const int n0 = j * 16;
-        ChanEpi ce[16];
-#pragma unroll
-        for (int x = 0; x < 16; ++x) ce[x] = make_chan_epi(sa, epi, slot, COUT, n0 + x, th, idx, s);
 #pragma unroll
         for (int mt = 0; mt < MTC; ++mt) {
             float v[16];
@@ -232,9 +233,9 @@ conv_tc_kernel(SlotArgs sa, int64_t off_w, LayerEpi epi, const void* __restrict_
             if (m < Cfg::M) {
                 float4* dst = reinterpret_cast<float4*>(out + (int64_t)m * COUT + n0);
 #pragma unroll
-                for (int x = 0; x < 16; x += 4)
-                    dst[x / 4] = make_float4(ce[x].apply(v[x]), ce[x + 1].apply(v[x + 1]), ce[x + 2].apply(v[x + 2]),
-                                             ce[x + 3].apply(v[x + 3]));
+                for (int x = 0; x < 16; x += 4)       // per-channel epilogue parameters come from shared memory
+                    dst[x / 4] = make_float4(epi_s[n0 + x].apply(v[x]), epi_s[n0 + x + 1].apply(v[x + 1]),
+                                             epi_s[n0 + x + 2].apply(v[x + 2]), epi_s[n0 + x + 3].apply(v[x + 3]));
             }
         }
     }
@@ -276,9 +277,9 @@ int dne_launch_conv_layer_tc(const SlotArgs& sa, const dne_layer_desc& L, const 
 #define ARGS sa, L, epi, in, in_slot_stride, in_img_stride, out, out_slot_stride, out_img_stride, n_slots, n_img, st
     if (in_u8 && tconv_is(L, 4, 32, 8, 4, 84, 21, 2)) return launch_conv_tc<4, 32, 8, 4, 84, 21, 2, true, 2, 16>(ARGS);
     if (in_u8 && tconv_is(L, 4, 16, 8, 4, 84, 21, 2)) return launch_conv_tc<4, 16, 8, 4, 84, 21, 2, true, 2, 16>(ARGS);
-    if (!in_u8 && tconv_is(L, 32, 64, 4, 2, 21, 11, 1)) return launch_conv_tc<32, 64, 4, 2, 21, 11, 1, false, 1, 32>(ARGS);
-    if (!in_u8 && tconv_is(L, 16, 32, 4, 2, 21, 11, 1)) return launch_conv_tc<16, 32, 4, 2, 21, 11, 1, false, 1, 32>(ARGS);
-    if (!in_u8 && tconv_is(L, 64, 64, 3, 1, 11, 11, 1)) return launch_conv_tc<64, 64, 3, 1, 11, 11, 1, false, 1, 32>(ARGS);
+    if (!in_u8 && tconv_is(L, 32, 64, 4, 2, 21, 11, 1)) return launch_conv_tc<32, 64, 4, 2, 21, 11, 1, false, 1, 16>(ARGS);
+    if (!in_u8 && tconv_is(L, 16, 32, 4, 2, 21, 11, 1)) return launch_conv_tc<16, 32, 4, 2, 21, 11, 1, false, 1, 16>(ARGS);
+    if (!in_u8 && tconv_is(L, 64, 64, 3, 1, 11, 11, 1)) return launch_conv_tc<64, 64, 3, 1, 11, 11, 1, false, 1, 16>(ARGS);
 #undef ARGS
     return DNE_ERR_UNSUP;
 }
