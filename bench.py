@@ -147,11 +147,12 @@ def run_b200(args):
     # +5% only -- the HBM-bound GEMV already fills every SM, so the halves time-slice instead of overlapping -- and it
     # makes per-kernel event timings overlap, so the roofline leg keeps the single-stream schedule).
     NS = int(os.environ.get("DNE_BENCH_STREAMS", "1"))
-    part = args.slots // NS
+    part = (args.slots // NS) // 2 * 2                          # whole antithetic pairs per table
     sfs = [SlotForward(ctx, net, part) for _ in range(NS)]
     streams = [torch.cuda.Stream(device=dev) for _ in range(NS)]
     PHASED = os.environ.get("DNE_BENCH_PHASED", "1") == "1"
-    phase_ev = [torch.cuda.Event() for _ in range(2)]
+    PHASE_MODE = int(os.environ.get("DNE_PHASE_MODE", "1" if NS > 2 else "0"))
+    phase_ev = [torch.cuda.Event() for _ in range(max(NS, 2))]
     for e in phase_ev:
         e.record()                                               # materialise the handles
     R = 4                                                        # observation pool blocks, rotated every tick
@@ -160,6 +161,15 @@ def run_b200(args):
     ret_acc = torch.zeros(args.slots, device=dev)
     idx_stream = np.random.RandomState(1)
     tally = {"launches": 0, "pairs": 0}
+    net_ref = C.byref(net.desc)
+    for sf in sfs:                                                # materialise the optional slot-table tensors once
+        sf.set_slots(np.zeros(part, np.int64), np.zeros(part, np.float32), active=np.ones(part, np.uint8))
+    fwd_args = [(F.ptr(sf.noise_idx), F.ptr(sf.scale), F.ptr(sf.active), F.ptr(sf.actions), F.ptr(sf.logits),
+                 F.ptr(sf.ws), sf.ws.numel()) for sf in sfs]
+    part_active = [False] * NS
+    obs_ptr = [[F.ptr(pool[r][h * part:(h + 1) * part]) for h in range(NS)] for r in range(R)]
+    stream_ptr = [C.c_void_p(s.cuda_stream) for s in streams]
+    ev_ptr = [C.c_void_p(e.cuda_event) for e in phase_ev]
 
     def generation_value():
         idx_all = np.array([noise.sample_index(idx_stream, P) for _ in range(n_pairs)], dtype=np.int64)
@@ -179,24 +189,30 @@ def run_b200(args):
                 ii = np.zeros(part, dtype=np.int64)
                 ii[:2 * k] = np.repeat(parts[h], 2)
                 sc = np.tile([SIGMA, -SIGMA], part // 2).astype(np.float32)
-                sfs[h].set_slots(ii, sc, active=act if 2 * k < part else None)
+                sfs[h].set_slots(ii, sc, active=act)
+                part_active[h] = 2 * k < part
             ret_acc.zero_()
             for s in streams:
                 s.wait_stream(cur)
+            # hot loop: raw C-ABI calls with pre-built ctypes arguments (no per-tick tensor slicing / stream context
+            # managers: at 4 slot tables the Python overhead of those was the bottleneck)
+            live = [h for h in range(NS) if len(parts[h]) > 0]
+            tally["launches"] += T * len(live)
+            tally["pairs"] += T * sum(len(parts[h]) for h in live)
+            fwd = L.dne_perturb_forward_conv
+            set_ev = L.dne_set_phase_events
+            theta_p = F.ptr(upd.theta)
             for t in range(T):
-                blk = pool[t % R]
-                for h in range(NS):
-                    if len(parts[h]) == 0:
-                        continue
-                    tally["launches"] += 1
-                    tally["pairs"] += len(parts[h])
-                    with torch.cuda.stream(streams[h]):
-                        if NS == 2 and PHASED:
-                            # table h waits for the OTHER table to reach its HBM-bound GEMV, then records its own
-                            F.check(L.dne_set_phase_events(ctx.handle, C.c_void_p(phase_ev[1 - h].cuda_event),
-                                                           C.c_void_p(phase_ev[h].cuda_event)))
-                        sfs[h].forward(upd.theta, blk[h * part:(h + 1) * part], paired=True)
-                        ret_acc[h * part:(h + 1) * part] += rew_pool[t % 64, h * part:(h + 1) * part]
+                r = t % R
+                for h in live:
+                    if NS >= 2 and PHASED:
+                        set_ev(ctx.handle, ev_ptr[(h - 1) % NS], ev_ptr[h], PHASE_MODE)
+                    a = fwd_args[h]
+                    rc = fwd(ctx.handle, net_ref, theta_p, a[0], a[1], None, a[2] if part_active[h] else None, part, 1,
+                             obs_ptr[r][h], None, a[3], a[4], a[5], a[6], stream_ptr[h])
+                    if rc:
+                        F.check(rc)
+                ret_acc.add_(rew_pool[t % 64])                     # one bookkeeping op per tick, main stream
             for s in streams:
                 cur.wait_stream(s)
             r = torch.cat([ret_acc[h * part:h * part + 2 * len(parts[h])] for h in range(NS)]).view(-1, 2)

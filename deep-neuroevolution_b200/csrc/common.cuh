@@ -25,6 +25,7 @@ struct dne_ctx {
     void* ev_wait;          // the forward's stream waits for this event before its first kernel
     void* ev_record;        // recorded right before the first HBM-bound noise GEMV of the call
     int ev_record_done;
+    int ev_mode;            // 0: wait before the first kernel, record before the GEMV; 1: wait before / record after the GEMV
 };
 extern unsigned long long g_dne_launches;   // kernels launched by this library (process-wide)
 #define DNE_LAUNCHED(n) (g_dne_launches += (unsigned long long)(n))

@@ -44,6 +44,7 @@ extern "C" int dne_ctx_create(int device, dne_ctx** out) {
     c->ev_cap = c->ev_n = c->prof_on = 0;
     c->ev_wait = c->ev_record = nullptr;
     c->ev_record_done = 0;
+    c->ev_mode = 0;
     cudaError_t e = cudaMalloc(&c->scratch, sizeof(double) * DNE_SCRATCH_DOUBLES);
     if (e != cudaSuccess) {
         delete c;
@@ -70,6 +71,7 @@ extern "C" int dne_ctx_destroy(dne_ctx* ctx) {
 extern "C" int dne_set_option(const char* name, int value) {
     DNE_CHECK_ARG(name, "name is null");
     if (strcmp(name, "conv_tc") == 0) { g_dne_conv_tc = value ? 1 : 0; return DNE_OK; }
+    if (strcmp(name, "dbg") == 0) { extern int g_dne_dbg; g_dne_dbg = value; return DNE_OK; }
     if (strcmp(name, "gemv_bulk") == 0) { g_dne_gemv_bulk = value ? 1 : 0; return DNE_OK; }
     if (strcmp(name, "gemv_ctas_per_sm") == 0 && value >= 1 && value <= 2) { g_dne_gemv_ctas_per_sm = value; return DNE_OK; }
     dne_set_error("dne_set_option: unknown option '%s'", name);
@@ -212,8 +214,10 @@ static int forward_impl(dne_ctx* ctx, const dne_net_desc* net, const float* d_th
 
     cudaStream_t st = (cudaStream_t)stream;
     // phase events (dne_set_phase_events): consumed by this call
-    if (ctx->ev_wait) DNE_CUDA(cudaStreamWaitEvent(st, (cudaEvent_t)ctx->ev_wait, 0));
-    ctx->ev_wait = nullptr;
+    if (ctx->ev_wait && ctx->ev_mode == 0) {
+        DNE_CUDA(cudaStreamWaitEvent(st, (cudaEvent_t)ctx->ev_wait, 0));
+        ctx->ev_wait = nullptr;
+    }
     ctx->ev_record_done = 0;
     char* ws = (char*)d_ws;
     SlotArgs sa;
@@ -278,6 +282,7 @@ static int forward_impl(dne_ctx* ctx, const dne_net_desc* net, const float* d_th
     }
     if (ctx->ev_record && !ctx->ev_record_done) DNE_CUDA(cudaEventRecord((cudaEvent_t)ctx->ev_record, st));
     ctx->ev_record = nullptr;
+    ctx->ev_wait = nullptr;
     return DNE_OK;
 }
 
@@ -285,11 +290,12 @@ static int forward_impl(dne_ctx* ctx, const dne_net_desc* net, const float* d_th
 // stream wait for `wait_event` (nullable) and records `record_event` (nullable) right before its first HBM-bound noise
 // GEMV.  With table A recording eA / waiting eB and table B recording eB / waiting eA, the compute-bound conv phase
 // of one table runs under the HBM-bound GEMV of the other instead of both tables doing the same phase in lockstep.
-extern "C" int dne_set_phase_events(dne_ctx* ctx, void* wait_event, void* record_event) {
-    DNE_CHECK_ARG(ctx, "ctx is null");
+extern "C" int dne_set_phase_events(dne_ctx* ctx, void* wait_event, void* record_event, int mode) {
+    DNE_CHECK_ARG(ctx && (mode == 0 || mode == 1), "bad arguments");
     ctx->ev_wait = wait_event;
     ctx->ev_record = record_event;
     ctx->ev_record_done = 0;
+    ctx->ev_mode = mode;
     return DNE_OK;
 }
 

@@ -593,9 +593,15 @@ int dne_launch_dense_layer(const dne_ctx* ctx, const SlotArgs& sa, const dne_lay
     }
     {
         GemvSrc ns{sa.noise, sa.noise_idx, nullptr, 0, L.off_w};
-        if (ctx->ev_record && !ctx->ev_record_done) {          // phase event: the HBM-bound part of this call starts
+        dne_ctx* mctx = const_cast<dne_ctx*>(ctx);
+        const bool first_gemv = !ctx->ev_record_done;
+        if (first_gemv && ctx->ev_mode == 0 && ctx->ev_record) {     // mode 0: the HBM-bound part of this call starts
             cudaEventRecord((cudaEvent_t)ctx->ev_record, st);
-            const_cast<dne_ctx*>(ctx)->ev_record_done = 1;
+            mctx->ev_record_done = 1;
+        }
+        if (first_gemv && ctx->ev_mode == 1 && ctx->ev_wait) {       // mode 1: take turns on the memory system
+            cudaStreamWaitEvent(st, (cudaEvent_t)ctx->ev_wait, 0);
+            mctx->ev_wait = nullptr;
         }
         const int groups = (n_slots + p.G - 1) / p.G;
         dim3 grid(p.n_chunks, groups);
@@ -612,6 +618,10 @@ int dne_launch_dense_layer(const dne_ctx* ctx, const SlotArgs& sa, const dne_lay
         if (prof) {
             cudaEventRecord(ctx->ev[2 * ctx->ev_n + 1], st);
             const_cast<dne_ctx*>(ctx)->ev_n++;
+        }
+        if (first_gemv && ctx->ev_mode == 1 && ctx->ev_record) {
+            cudaEventRecord((cudaEvent_t)ctx->ev_record, st);
+            mctx->ev_record_done = 1;
         }
     }
     {

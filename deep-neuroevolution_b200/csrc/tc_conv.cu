@@ -17,7 +17,9 @@
 
 using namespace tc05;
 
-constexpr int TC_THREADS = 256;
+int g_dne_dbg = 0;                   // debug mask for conv_tc_kernel timing experiments (dne_set_option("dbg", mask))
+constexpr int TC_THREADS = 512;      // conv kernels: 16 warps halve the per-thread staging chain (the CTA's latency IS the kernel time)
+constexpr int TG_THREADS = 256;      // theta GEMM / self-test
 
 template <int CIN, int COUT, int KS, int STRIDE, int HIN, int HOUT, int PAD, bool IN_U8, int MTC, int KC>
 struct TcConvCfg {
@@ -31,14 +33,19 @@ struct TcConvCfg {
     static constexpr int B_BYTES = (KC / 4) * B_PLANE;
     static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
     static constexpr int SMEM_BYTES = 2 * STAGE_BYTES + 128;     // + alignment slack
-    static constexpr int TMEM_COLS = (MTC * COUT <= 32) ? 32 : (MTC * COUT <= 64) ? 64 : (MTC * COUT <= 128) ? 128 : 256;
+    // three independent accumulators per M tile (hi*hi, lo*hi, hi*lo): consecutive MMAs never wait on each other's
+    // result (a dependent accumulate chain of tiny N x K=8 MMAs is latency bound); summed in the epilogue
+    static constexpr int NACC = 3;
+    static constexpr int ACC_COLS = NACC * MTC * COUT;
+    static constexpr int TMEM_COLS = (ACC_COLS <= 32) ? 32 : (ACC_COLS <= 64) ? 64 : (ACC_COLS <= 128) ? 128 : (ACC_COLS <= 256) ? 256 : 512;
     static_assert(K % KC == 0 && KC % 8 == 0 && CIN % 4 == 0 && COUT % 16 == 0, "tile constraints");
 };
 
 template <int CIN, int COUT, int KS, int STRIDE, int HIN, int HOUT, int PAD, bool IN_U8, int MTC, int KC>
-__global__ void __launch_bounds__(TC_THREADS, 3)
+__global__ void __launch_bounds__(TC_THREADS, 2)
 conv_tc_kernel(SlotArgs sa, int64_t off_w, LayerEpi epi, const void* __restrict__ in_base, int64_t in_slot_stride,
-               int64_t in_img_stride, float* __restrict__ out_base, int64_t out_slot_stride, int64_t out_img_stride) {
+               int64_t in_img_stride, float* __restrict__ out_base, int64_t out_slot_stride, int64_t out_img_stride,
+               int dbg) {
     using Cfg = TcConvCfg<CIN, COUT, KS, STRIDE, HIN, HOUT, PAD, IN_U8, MTC, KC>;
     const int slot = blockIdx.y;
     if (!slot_active(sa, slot)) return;
@@ -122,7 +129,7 @@ conv_tc_kernel(SlotArgs sa, int64_t off_w, LayerEpi epi, const void* __restrict_
             const int ci = k % CIN, t = k / CIN;
             const int kx = t % KS, ky = t / KS;
             const int iy = a_iy0[i] + ky, ix = a_ix0[i] + kx;
-            const bool ok = a_ok[i] && iy >= 0 && iy < HIN && ix >= 0 && ix < HIN;
+            const bool ok = a_ok[i] && iy >= 0 && iy < HIN && ix >= 0 && ix < HIN && !(dbg & 2);
             const int e = (iy * HIN + ix) * CIN + ci;
             if (IN_U8) rawA_u8[IN_U8 ? i : 0] = ok ? *reinterpret_cast<const uint32_t*>(in_u8 + e) : 0u;
             else rawA_f[IN_U8 ? 0 : i] = ok ? *reinterpret_cast<const float4*>(in_f + e) : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -130,7 +137,7 @@ conv_tc_kernel(SlotArgs sa, int64_t off_w, LayerEpi epi, const void* __restrict_
 #pragma unroll
         for (int i = 0; i < B_PER_THREAD; ++i) {
             const int u = tid + i * TC_THREADS;
-            if (u < B_UNITS) {
+            if (u < B_UNITS && !(dbg & 4)) {
                 const int n = u % COUT, q = u / COUT;
                 const int64_t f = (int64_t)(k0 + 4 * q) * COUT + n;
 #pragma unroll
@@ -190,12 +197,13 @@ conv_tc_kernel(SlotArgs sa, int64_t off_w, LayerEpi epi, const void* __restrict_
         if (c + 1 < Cfg::NCHUNK) load_chunk(c + 1);               // in flight across the fence / barrier / MMA issue
         fence_proxy_async_smem();          // generic-proxy writes -> async proxy (tensor core reads)
         __syncthreads();
-        if (tid == 0) {
+        if (tid == 0 && (dbg & 1)) mma_commit(&bars[st]);
+        if (tid == 0 && !(dbg & 1)) {
             fence_after_thread_sync();
             const uint32_t aH = smem_u32(sA_hi), aL = smem_u32(sA_lo), bH = smem_u32(sB_hi), bL = smem_u32(sB_lo);
 #pragma unroll
             for (int mt = 0; mt < MTC; ++mt) {
-                const uint32_t d = tmem_base + mt * COUT;
+                const uint32_t d = tmem_base + mt * (Cfg::NACC * COUT);
 #pragma unroll
                 for (int k8 = 0; k8 < KC / 8; ++k8) {
                     const uint32_t ao = 2 * k8 * Cfg::A_PLANE + mt * 128 * 16;
@@ -203,8 +211,8 @@ conv_tc_kernel(SlotArgs sa, int64_t off_w, LayerEpi epi, const void* __restrict_
                     const uint64_t dAh = smem_desc(aH + ao, Cfg::A_PLANE, 128), dAl = smem_desc(aL + ao, Cfg::A_PLANE, 128);
                     const uint64_t dBh = smem_desc(bH + bo, Cfg::B_PLANE, 128), dBl = smem_desc(bL + bo, Cfg::B_PLANE, 128);
                     mma_tf32(d, dAh, dBh, IDESC, (c | k8) != 0);
-                    mma_tf32(d, dAl, dBh, IDESC, 1);
-                    mma_tf32(d, dAh, dBl, IDESC, 1);
+                    mma_tf32(d + COUT, dAl, dBh, IDESC, (c | k8) != 0);
+                    mma_tf32(d + 2 * COUT, dAh, dBl, IDESC, (c | k8) != 0);
                 }
             }
             mma_commit(&bars[st]);
@@ -219,24 +227,28 @@ conv_tc_kernel(SlotArgs sa, int64_t off_w, LayerEpi epi, const void* __restrict_
 
     // ---- epilogue: TMEM -> registers -> bias (+BN) + activation -> NHWC global ----
     float* out = out_base + slot * out_slot_stride + img * out_img_stride;
-    const int lg = warp & 3, ch = warp >> 2;                      // TMEM lane group of this warp; column-group parity
+    // warp w may only touch TMEM lanes 32*(w%4)..+31; the (M-tile, 16-column group) work items are dealt round-robin to
+    // the TC_THREADS/128 warps that share a lane group
+    const int lg = warp & 3, wslot = warp >> 2;
+    constexpr int NSLOT = TC_THREADS / 128, NJ = COUT / 16;
 #pragma unroll
-    for (int j = 0; j < COUT / 16; ++j) {
-        if ((j & 1) != ch && COUT > 16) continue;                 // warps w and w+4 share lanes: split the column groups
-        if (COUT == 16 && ch != 0) continue;
-        const int n0 = j * 16;
+    for (int p = 0; p < MTC * NJ; ++p) {
+        if (p % NSLOT != wslot) continue;
+        const int mt = p / NJ, n0 = (p % NJ) * 16;
+        float v[16], v1[16], v2[16];
+        const uint32_t ta = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(mt * (Cfg::NACC * COUT) + n0);
+        tmem_ld16(ta, v);
+        tmem_ld16(ta + COUT, v1);
+        tmem_ld16(ta + 2 * COUT, v2);
 #pragma unroll
-        for (int mt = 0; mt < MTC; ++mt) {
-            float v[16];
-            tmem_ld16(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(mt * COUT + n0), v);
-            const int m = row0 + mt * 128 + lg * 32 + lane;
-            if (m < Cfg::M) {
-                float4* dst = reinterpret_cast<float4*>(out + (int64_t)m * COUT + n0);
+        for (int x = 0; x < 16; ++x) v[x] += v1[x] + v2[x];      // small correction terms first
+        const int m = row0 + mt * 128 + lg * 32 + lane;
+        if (m < Cfg::M && !(dbg & 8)) {
+            float4* dst = reinterpret_cast<float4*>(out + (int64_t)m * COUT + n0);
 #pragma unroll
-                for (int x = 0; x < 16; x += 4)       // per-channel epilogue parameters come from shared memory
-                    dst[x / 4] = make_float4(epi_s[n0 + x].apply(v[x]), epi_s[n0 + x + 1].apply(v[x + 1]),
-                                             epi_s[n0 + x + 2].apply(v[x + 2]), epi_s[n0 + x + 3].apply(v[x + 3]));
-            }
+            for (int x = 0; x < 16; x += 4)       // per-channel epilogue parameters come from shared memory
+                dst[x / 4] = make_float4(epi_s[n0 + x].apply(v[x]), epi_s[n0 + x + 1].apply(v[x + 1]),
+                                         epi_s[n0 + x + 2].apply(v[x + 2]), epi_s[n0 + x + 3].apply(v[x + 3]));
         }
     }
     fence_before_thread_sync();
@@ -260,7 +272,7 @@ static int launch_conv_tc(const SlotArgs& sa, const dne_layer_desc& L, const Lay
     }
     dim3 grid((Cfg::M + Cfg::ROWS - 1) / Cfg::ROWS, n_slots, n_img);
     kern<<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(sa, L.off_w, epi, in, in_slot_stride, in_img_stride, out,
-                                                   out_slot_stride, out_img_stride);
+                                                   out_slot_stride, out_img_stride, g_dne_dbg);
     DNE_LAUNCHED(1);
     return 0;
 }
@@ -389,7 +401,7 @@ constexpr int TG_A_BYTES = (TG_KC / 4) * TG_A_PLANE, TG_B_BYTES = (TG_KC / 4) * 
 constexpr int TG_STAGE_BYTES = 2 * TG_A_BYTES + 2 * TG_B_BYTES;
 constexpr int TG_SMEM_BYTES = 2 * TG_STAGE_BYTES + 128;
 
-__global__ void __launch_bounds__(TC_THREADS)
+__global__ void __launch_bounds__(TG_THREADS)
 theta_gemm_tc_kernel(const float* __restrict__ X, int M, int K, int N, const float* __restrict__ W, int k_per_split,
                      float* __restrict__ part) {
     extern __shared__ uint8_t smem_raw[];
@@ -420,7 +432,7 @@ theta_gemm_tc_kernel(const float* __restrict__ X, int M, int K, int N, const flo
         const int k0 = kbeg + c * TG_KC;
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
-            const int u = tid + i * TC_THREADS;
+            const int u = tid + i * TG_THREADS;
             const int r = u % TG_BM, q = u / TG_BM;
             const int m = m0 + r, k = k0 + 4 * q;
             rawA[i] = (m < M && k < kend) ? *reinterpret_cast<const float4*>(X + (int64_t)m * K + k)
@@ -440,7 +452,7 @@ theta_gemm_tc_kernel(const float* __restrict__ X, int M, int K, int N, const flo
         uint8_t* sB_lo = sB_hi + TG_B_BYTES;
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
-            const int u = tid + i * TC_THREADS;
+            const int u = tid + i * TG_THREADS;
             float4 hi, lo;
             split_tf32_fast(rawA[i].x, hi.x, lo.x);
             split_tf32_fast(rawA[i].y, hi.y, lo.y);
@@ -516,6 +528,6 @@ int dne_launch_theta_gemm_tc(const float* X, int M, int K, int N, const float* W
         attr_done = true;
     }
     dim3 grid((N + TG_BN - 1) / TG_BN, (M + TG_BM - 1) / TG_BM, n_split);
-    theta_gemm_tc_kernel<<<grid, TC_THREADS, TG_SMEM_BYTES, st>>>(X, M, K, N, W, k_per_split, part);
+    theta_gemm_tc_kernel<<<grid, TG_THREADS, TG_SMEM_BYTES, st>>>(X, M, K, N, W, k_per_split, part);
     return 0;
 }

@@ -128,8 +128,10 @@ int dne_perturb_forward_conv(dne_ctx* ctx, const dne_net_desc* net, const float*
 /* Phase-shifted double buffering of two slot tables on two CUDA streams: the NEXT dne_perturb_forward_* call on ctx
  * makes its stream wait for wait_event (cudaEvent_t, nullable) before its first kernel and records record_event
  * (nullable) right before its first HBM-bound noise GEMV.  Table A: (wait eB, record eA); table B: (wait eA, record eB):
- * the tensor-core conv phase of one table then runs under the HBM-bound phase of the other. */
-int dne_set_phase_events(dne_ctx* ctx, void* wait_event, void* record_event);
+ * the tensor-core conv phase of one table then runs under the HBM-bound phase of the other (mode 0).
+ * mode 1 instead waits right before the GEMV and records right after it: the tables take turns on the memory system
+ * while their conv chains free-run (use with >= 3 tables). */
+int dne_set_phase_events(dne_ctx* ctx, void* wait_event, void* record_event, int mode);
 
 /* MujocoPolicy variant (policies.py:150-162,195-196,202-206): float observations, ob normalisation, tanh MLP,
  * continuous head.  d_actions_out float[n_slots, n_out] (action noise is added by the caller's stream). */
