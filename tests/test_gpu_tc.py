@@ -132,3 +132,39 @@ def test_ga_slots_parent_rows(ctx, host_noise, paired):
                               obs[s:s + 1])[0][0] for s in range(n_slots)])
     bound = 2e-5 * max(1.0, float(np.abs(ref).max()))
     assert np.abs(logits - ref).max() <= bound, np.abs(logits - ref).max()
+
+
+def test_two_tables_with_phase_events_match_single_table(ctx, host_noise):
+    """Two slot tables on two streams with phase events (both modes) compute exactly what one table computes."""
+    net = N.make_net("Model")
+    P = net.num_params
+    rs = np.random.RandomState(77)
+    theta = cuda((rs.randn(P) * 0.05).astype(np.float32))
+    n = 8
+    pidx = rs.randint(0, NOISE_COUNT - P + 1, size=n // 2).astype(np.int64)
+    idx, scale = np.repeat(pidx, 2), np.tile([0.02, -0.02], n // 2).astype(np.float32)
+    obs = cuda(rs.randint(0, 256, size=(n, 84, 84, 4)).astype(np.uint8))
+    whole = SlotForward(ctx, net, n)
+    whole.set_slots(idx, scale)
+    whole.forward(theta, obs, paired=1)
+    ref_logits, ref_actions = whole.logits.clone(), whole.actions.clone()
+    half = n // 2
+    tabs = [SlotForward(ctx, net, half) for _ in range(2)]
+    streams = [torch.cuda.Stream() for _ in range(2)]
+    evs = [torch.cuda.Event() for _ in range(2)]
+    for e in evs:
+        e.record()
+    for h in range(2):
+        tabs[h].set_slots(idx[h * half:(h + 1) * half], scale[h * half:(h + 1) * half])
+    torch.cuda.synchronize()
+    for mode in (0, 1):
+        for rep in range(3):
+            for h in range(2):
+                with torch.cuda.stream(streams[h]):
+                    F.check(F.lib().dne_set_phase_events(ctx.handle, C.c_void_p(evs[1 - h].cuda_event),
+                                                         C.c_void_p(evs[h].cuda_event), mode))
+                    tabs[h].forward(theta, obs[h * half:(h + 1) * half], paired=1)
+        torch.cuda.synchronize()
+        got = torch.cat([tabs[0].logits, tabs[1].logits])
+        assert torch.equal(got, ref_logits), mode
+        assert torch.equal(torch.cat([tabs[0].actions, tabs[1].actions]), ref_actions)
