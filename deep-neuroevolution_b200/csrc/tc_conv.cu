@@ -18,7 +18,8 @@
 using namespace tc05;
 
 int g_dne_dbg = 0;                   // debug mask for conv_tc_kernel timing experiments (dne_set_option("dbg", mask))
-constexpr int TC_THREADS = 512;      // conv kernels: 16 warps halve the per-thread staging chain (the CTA's latency IS the kernel time)
+constexpr int TC_THREADS = 512;      // conv kernels: 16 staging warps ...
+constexpr int TC_BLOCK = TC_THREADS + 32;   // ... + one MMA-issuing warp (warp-specialised, mbarrier pipeline, no block barriers)
 constexpr int TG_THREADS = 256;      // theta GEMM / self-test
 
 template <int CIN, int COUT, int KS, int STRIDE, int HIN, int HOUT, int PAD, bool IN_U8, int MTC, int KC>
@@ -32,7 +33,9 @@ struct TcConvCfg {
     static constexpr int A_BYTES = (KC / 4) * A_PLANE;           // one of {hi, lo}
     static constexpr int B_BYTES = (KC / 4) * B_PLANE;
     static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
-    static constexpr int SMEM_BYTES = 2 * STAGE_BYTES + 128;     // + alignment slack
+    static constexpr int NST = 3;                                // shared-memory stages (staging warps run ahead of the MMA warp)
+    static constexpr int PF = 2;                                 // chunks of raw global loads in flight per thread
+    static constexpr int SMEM_BYTES = NST * STAGE_BYTES + 128;   // + alignment slack
     // three independent accumulators per M tile (hi*hi, lo*hi, hi*lo): consecutive MMAs never wait on each other's
     // result (a dependent accumulate chain of tiny N x K=8 MMAs is latency bound); summed in the epilogue
     static constexpr int NACC = 3;
@@ -42,7 +45,7 @@ struct TcConvCfg {
 };
 
 template <int CIN, int COUT, int KS, int STRIDE, int HIN, int HOUT, int PAD, bool IN_U8, int MTC, int KC>
-__global__ void __launch_bounds__(TC_THREADS, 2)
+__global__ void __launch_bounds__(TC_BLOCK, 2)
 conv_tc_kernel(SlotArgs sa, int64_t off_w, LayerEpi epi, const void* __restrict__ in_base, int64_t in_slot_stride,
                int64_t in_img_stride, float* __restrict__ out_base, int64_t out_slot_stride, int64_t out_img_stride,
                int dbg) {
@@ -52,203 +55,216 @@ conv_tc_kernel(SlotArgs sa, int64_t off_w, LayerEpi epi, const void* __restrict_
     const int img = blockIdx.z;
     const int row0 = blockIdx.x * Cfg::ROWS;                     // first output position of this CTA
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    constexpr int NST = Cfg::NST;
+    constexpr int STAGE_WARPS = TC_THREADS / 32;
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
-    __shared__ uint64_t bars[2];
+    __shared__ uint64_t full_bar[NST], empty_bar[NST], done_bar;
     __shared__ uint32_t tmem_base_s;
+    __shared__ ChanEpi epi_s[COUT];                              // per-channel epilogue parameters, built once per CTA
+    __shared__ float2 u8_lut[IN_U8 ? 256 : 1];                   // uint8 -> (hi, lo) of value/255 (atari_wrappers.py:186)
+
+    const float* th = slot_theta(sa, slot);
+    const int64_t idx = sa.noise_idx[slot];
+    const float s = sa.scale[slot];
 
     if (warp == 0) tmem_alloc(&tmem_base_s, Cfg::TMEM_COLS);
     if (tid == 32) {
-        mbar_init(&bars[0], 1);
-        mbar_init(&bars[1], 1);
+        for (int i = 0; i < NST; ++i) {
+            mbar_init(&full_bar[i], STAGE_WARPS);                // one arrival per staging warp
+            mbar_init(&empty_bar[i], 1);                         // tcgen05.commit of the MMA warp
+        }
+        mbar_init(&done_bar, 1);
         fence_mbar_init();
+    }
+    if (tid < COUT) epi_s[tid] = make_chan_epi(sa, epi, slot, COUT, tid, th, idx, s);
+    if (IN_U8 && tid >= 256 && tid < 512) {
+        const float v = __fdiv_rn((float)(tid - 256), 255.0f);
+        float hi, lo;
+        split_tf32_fast(v, hi, lo);
+        u8_lut[IN_U8 ? tid - 256 : 0] = make_float2(hi, lo);
     }
     fence_before_thread_sync();
     __syncthreads();
     fence_after_thread_sync();
     const uint32_t tmem_base = tmem_base_s;
-
-    const float* th = slot_theta(sa, slot);
-    const int64_t idx = sa.noise_idx[slot];
-    const float s = sa.scale[slot];
-    const float* nz = sa.noise + idx + off_w;
-    const float* tw = th + off_w;
-    const uint8_t* in_u8 = nullptr;
-    const float* in_f = nullptr;
-    if (IN_U8) in_u8 = (const uint8_t*)in_base + slot * in_slot_stride + img * in_img_stride;
-    else in_f = (const float*)in_base + slot * in_slot_stride + img * in_img_stride;
-
-    // A staging units of this thread: (row r, k-quad q), r fastest.  r is fixed per unit index across chunks.
-    constexpr int A_UNITS = Cfg::ROWS * (KC / 4);
-    constexpr int A_PER_THREAD = A_UNITS / TC_THREADS;
-    static_assert(A_UNITS % TC_THREADS == 0 && Cfg::ROWS % TC_THREADS == 0 || TC_THREADS % Cfg::ROWS == 0, "A staging map");
-    int a_iy0[A_PER_THREAD], a_ix0[A_PER_THREAD];
-    bool a_ok[A_PER_THREAD];
-#pragma unroll
-    for (int i = 0; i < A_PER_THREAD; ++i) {
-        const int u = tid + i * TC_THREADS;
-        const int m = row0 + (u % Cfg::ROWS);
-        a_ok[i] = m < Cfg::M;
-        a_iy0[i] = (m / HOUT) * STRIDE - PAD;
-        a_ix0[i] = (m % HOUT) * STRIDE - PAD;
-    }
-    constexpr int B_UNITS = COUT * (KC / 4);
-    constexpr int B_PER_THREAD = (B_UNITS + TC_THREADS - 1) / TC_THREADS;
-
     constexpr uint32_t IDESC = idesc_tf32(128, COUT);
 
-    // per-output-channel epilogue parameters (perturbed bias, virtual-BN statistics / scale / shift) built once per CTA
-    __shared__ ChanEpi epi_s[COUT];
-    if (tid < COUT) epi_s[tid] = make_chan_epi(sa, epi, slot, COUT, tid, th, idx, s);
-
-    // uint8 observations: value/255 and its hi/lo TF32 split come from a 256-entry table (no IEEE division per pixel)
-    __shared__ float2 u8_lut[IN_U8 ? 256 : 1];
-    if (IN_U8) {
-        if (tid < 256) {
-            const float v = __fdiv_rn((float)tid, 255.0f);        // atari_wrappers.py:186
-            float hi, lo;
-            split_tf32_fast(v, hi, lo);
-            u8_lut[tid] = make_float2(hi, lo);
+    if (warp == STAGE_WARPS) {
+        // =========================== MMA warp: one lane feeds the tensor core ===========================
+        if (lane == 0) {
+            for (int c = 0; c < Cfg::NCHUNK; ++c) {
+                const int st = c % NST;
+                mbar_wait(&full_bar[st], (c / NST) & 1);         // the staging warps have filled (and fenced) this stage
+                fence_after_thread_sync();
+                if (!(dbg & 1)) {
+                    const uint32_t aH = smem_u32(smem + st * Cfg::STAGE_BYTES), aL = aH + Cfg::A_BYTES,
+                                   bH = aL + Cfg::A_BYTES, bL = bH + Cfg::B_BYTES;
+#pragma unroll
+                    for (int mt = 0; mt < MTC; ++mt) {
+                        const uint32_t d = tmem_base + mt * (Cfg::NACC * COUT);
+#pragma unroll
+                        for (int k8 = 0; k8 < KC / 8; ++k8) {
+                            const uint32_t ao = 2 * k8 * Cfg::A_PLANE + mt * 128 * 16;
+                            const uint32_t bo = 2 * k8 * Cfg::B_PLANE;
+                            const uint64_t dAh = smem_desc(aH + ao, Cfg::A_PLANE, 128), dAl = smem_desc(aL + ao, Cfg::A_PLANE, 128);
+                            const uint64_t dBh = smem_desc(bH + bo, Cfg::B_PLANE, 128), dBl = smem_desc(bL + bo, Cfg::B_PLANE, 128);
+                            mma_tf32(d, dAh, dBh, IDESC, (c | k8) != 0);
+                            mma_tf32(d + COUT, dAl, dBh, IDESC, (c | k8) != 0);
+                            mma_tf32(d + 2 * COUT, dAh, dBl, IDESC, (c | k8) != 0);
+                        }
+                    }
+                }
+                mma_commit(&empty_bar[st]);                      // stage reusable once these MMAs have read it
+            }
+            mma_commit(&done_bar);                               // every MMA of the tile has completed
         }
-        __syncthreads();
-    }
+    } else {
+        // =========================== staging warps: perturb + im2col -> shared memory =====================
+        const float* nz = sa.noise + idx + off_w;
+        const float* tw = th + off_w;
+        const uint8_t* in_u8 = nullptr;
+        const float* in_f = nullptr;
+        if (IN_U8) in_u8 = (const uint8_t*)in_base + slot * in_slot_stride + img * in_img_stride;
+        else in_f = (const float*)in_base + slot * in_slot_stride + img * in_img_stride;
 
-    // Software pipeline: the raw global loads of chunk c+1 are issued (into registers) while chunk c is converted,
-    // stored, fenced and handed to the tensor core, so their latency overlaps the barrier and the MMA issue.
-    uint32_t rawA_u8[IN_U8 ? A_PER_THREAD : 1];
-    float4 rawA_f[IN_U8 ? 1 : A_PER_THREAD];
-    float rawB_t[B_PER_THREAD][4], rawB_n[B_PER_THREAD][4];
-    auto load_chunk = [&](int c) {
-        const int k0 = c * KC;
+        // A staging units of this thread: (row r, k-quad q), r fastest; r is fixed per unit index across chunks
+        constexpr int A_UNITS = Cfg::ROWS * (KC / 4);
+        constexpr int A_PER_THREAD = A_UNITS / TC_THREADS;
+        static_assert(A_UNITS % TC_THREADS == 0 && (Cfg::ROWS % TC_THREADS == 0 || TC_THREADS % Cfg::ROWS == 0), "A staging map");
+        int a_iy0[A_PER_THREAD], a_ix0[A_PER_THREAD];
+        bool a_ok[A_PER_THREAD];
 #pragma unroll
         for (int i = 0; i < A_PER_THREAD; ++i) {
             const int u = tid + i * TC_THREADS;
-            const int q = u / Cfg::ROWS;
-            const int k = k0 + 4 * q;
-            const int ci = k % CIN, t = k / CIN;
-            const int kx = t % KS, ky = t / KS;
-            const int iy = a_iy0[i] + ky, ix = a_ix0[i] + kx;
-            const bool ok = a_ok[i] && iy >= 0 && iy < HIN && ix >= 0 && ix < HIN && !(dbg & 2);
-            const int e = (iy * HIN + ix) * CIN + ci;
-            if (IN_U8) rawA_u8[IN_U8 ? i : 0] = ok ? *reinterpret_cast<const uint32_t*>(in_u8 + e) : 0u;
-            else rawA_f[IN_U8 ? 0 : i] = ok ? *reinterpret_cast<const float4*>(in_f + e) : make_float4(0.f, 0.f, 0.f, 0.f);
+            const int m = row0 + (u % Cfg::ROWS);
+            a_ok[i] = m < Cfg::M;
+            a_iy0[i] = (m / HOUT) * STRIDE - PAD;
+            a_ix0[i] = (m % HOUT) * STRIDE - PAD;
         }
+        constexpr int B_UNITS = COUT * (KC / 4);
+        constexpr int B_PER_THREAD = (B_UNITS + TC_THREADS - 1) / TC_THREADS;
+
+        // Register software pipeline: the raw global loads of chunk c+PF are in flight while chunk c is converted
+        constexpr int PF = Cfg::PF;
+        uint32_t rawA_u8[PF][IN_U8 ? A_PER_THREAD : 1];
+        float4 rawA_f[PF][IN_U8 ? 1 : A_PER_THREAD];
+        float rawB_t[PF][B_PER_THREAD][4], rawB_n[PF][B_PER_THREAD][4];
+        auto load_chunk = [&](int c, int slot_) {
+            const int k0 = c * KC;
 #pragma unroll
-        for (int i = 0; i < B_PER_THREAD; ++i) {
-            const int u = tid + i * TC_THREADS;
-            if (u < B_UNITS && !(dbg & 4)) {
-                const int n = u % COUT, q = u / COUT;
-                const int64_t f = (int64_t)(k0 + 4 * q) * COUT + n;
+            for (int i = 0; i < A_PER_THREAD; ++i) {
+                const int u = tid + i * TC_THREADS;
+                const int q = u / Cfg::ROWS;
+                const int k = k0 + 4 * q;
+                const int ci = k % CIN, t = k / CIN;
+                const int kx = t % KS, ky = t / KS;
+                const int iy = a_iy0[i] + ky, ix = a_ix0[i] + kx;
+                const bool ok = a_ok[i] && iy >= 0 && iy < HIN && ix >= 0 && ix < HIN && !(dbg & 2);
+                const int e = (iy * HIN + ix) * CIN + ci;
+                if (IN_U8) rawA_u8[slot_][IN_U8 ? i : 0] = ok ? *reinterpret_cast<const uint32_t*>(in_u8 + e) : 0u;
+                else rawA_f[slot_][IN_U8 ? 0 : i] = ok ? *reinterpret_cast<const float4*>(in_f + e) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    rawB_t[i][j] = tw[f + j * COUT];
-                    rawB_n[i][j] = nz[f + j * COUT];
+            for (int i = 0; i < B_PER_THREAD; ++i) {
+                const int u = tid + i * TC_THREADS;
+                if (u < B_UNITS && !(dbg & 4)) {
+                    const int n = u % COUT, q = u / COUT;
+                    const int64_t f = (int64_t)(k0 + 4 * q) * COUT + n;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        rawB_t[slot_][i][j] = tw[f + j * COUT];
+                        rawB_n[slot_][i][j] = nz[f + j * COUT];
+                    }
+                }
+            }
+        };
+#pragma unroll
+        for (int p = 0; p < PF; ++p)
+            if (p < Cfg::NCHUNK) load_chunk(p, p);
+
+        // the chunk loop is unrolled by PF so that the register ring is indexed statically
+        for (int c0 = 0; c0 < Cfg::NCHUNK; c0 += PF) {
+#pragma unroll
+            for (int p = 0; p < PF; ++p) {
+                const int c = c0 + p;
+                if (c < Cfg::NCHUNK) {
+                    const int st = c % NST;
+                    mbar_wait(&empty_bar[st], ((c / NST) & 1) ^ 1);      // MMAs of chunk c-NST have drained this stage
+                    uint8_t* sA_hi = smem + st * Cfg::STAGE_BYTES;
+                    uint8_t* sA_lo = sA_hi + Cfg::A_BYTES;
+                    uint8_t* sB_hi = sA_lo + Cfg::A_BYTES;
+                    uint8_t* sB_lo = sB_hi + Cfg::B_BYTES;
+#pragma unroll
+                    for (int i = 0; i < A_PER_THREAD; ++i) {
+                        const int u = tid + i * TC_THREADS;
+                        const int r = u % Cfg::ROWS, q = u / Cfg::ROWS;
+                        float4 hi, lo;
+                        if (IN_U8) {
+                            const uint32_t px = rawA_u8[p][IN_U8 ? i : 0];
+                            const float2 e0 = u8_lut[px & 255u], e1 = u8_lut[(px >> 8) & 255u],
+                                         e2 = u8_lut[(px >> 16) & 255u], e3 = u8_lut[IN_U8 ? (px >> 24) : 0];
+                            hi = make_float4(e0.x, e1.x, e2.x, e3.x);
+                            lo = make_float4(e0.y, e1.y, e2.y, e3.y);
+                        } else {
+                            const float4 v = rawA_f[p][IN_U8 ? 0 : i];
+                            split_tf32_fast(v.x, hi.x, lo.x);
+                            split_tf32_fast(v.y, hi.y, lo.y);
+                            split_tf32_fast(v.z, hi.z, lo.z);
+                            split_tf32_fast(v.w, hi.w, lo.w);
+                        }
+                        *reinterpret_cast<float4*>(sA_hi + q * Cfg::A_PLANE + r * 16) = hi;
+                        *reinterpret_cast<float4*>(sA_lo + q * Cfg::A_PLANE + r * 16) = lo;
+                    }
+#pragma unroll
+                    for (int i = 0; i < B_PER_THREAD; ++i) {
+                        const int u = tid + i * TC_THREADS;
+                        if (u < B_UNITS) {
+                            const int n = u % COUT, q = u / COUT;
+                            float4 hi, lo;
+                            split_tf32_fast(perturbed(rawB_t[p][i][0], s, rawB_n[p][i][0]), hi.x, lo.x);
+                            split_tf32_fast(perturbed(rawB_t[p][i][1], s, rawB_n[p][i][1]), hi.y, lo.y);
+                            split_tf32_fast(perturbed(rawB_t[p][i][2], s, rawB_n[p][i][2]), hi.z, lo.z);
+                            split_tf32_fast(perturbed(rawB_t[p][i][3], s, rawB_n[p][i][3]), hi.w, lo.w);
+                            *reinterpret_cast<float4*>(sB_hi + q * Cfg::B_PLANE + n * 16) = hi;
+                            *reinterpret_cast<float4*>(sB_lo + q * Cfg::B_PLANE + n * 16) = lo;
+                        }
+                    }
+                    if (c + PF < Cfg::NCHUNK) load_chunk(c + PF, p);     // refill this ring slot
+                    fence_proxy_async_smem();                            // generic-proxy writes -> async proxy
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&full_bar[st]);
                 }
             }
         }
-    };
-    load_chunk(0);
-
-    for (int c = 0; c < Cfg::NCHUNK; ++c) {
-        const int st = c & 1;
-        if (c >= 2) mbar_wait(&bars[st], ((c >> 1) - 1) & 1);     // MMAs of chunk c-2 finished reading this stage
-        uint8_t* sA_hi = smem + st * Cfg::STAGE_BYTES;
-        uint8_t* sA_lo = sA_hi + Cfg::A_BYTES;
-        uint8_t* sB_hi = sA_lo + Cfg::A_BYTES;
-        uint8_t* sB_lo = sB_hi + Cfg::B_BYTES;
-        // ---- stage A: hi/lo split of the im2col values loaded one iteration ago ----
+        // ---- epilogue: TMEM -> registers -> bias (+BN) + activation -> NHWC global ----
+        mbar_wait(&done_bar, 0);
+        fence_after_thread_sync();
+        float* out = out_base + slot * out_slot_stride + img * out_img_stride;
+        // warp w may only touch TMEM lanes 32*(w%4)..+31; the (M-tile, 16-column group) work items are dealt round-robin
+        // to the TC_THREADS/128 warps that share a lane group
+        const int lg = warp & 3, wslot = warp >> 2;
+        constexpr int NSLOT = TC_THREADS / 128, NJ = COUT / 16;
 #pragma unroll
-        for (int i = 0; i < A_PER_THREAD; ++i) {
-            const int u = tid + i * TC_THREADS;
-            const int r = u % Cfg::ROWS, q = u / Cfg::ROWS;
-            float4 hi, lo;
-            if (IN_U8) {
-                const uint32_t p = rawA_u8[IN_U8 ? i : 0];
-                const float2 e0 = u8_lut[p & 255u], e1 = u8_lut[(p >> 8) & 255u], e2 = u8_lut[(p >> 16) & 255u],
-                             e3 = u8_lut[IN_U8 ? (p >> 24) : 0];
-                hi = make_float4(e0.x, e1.x, e2.x, e3.x);
-                lo = make_float4(e0.y, e1.y, e2.y, e3.y);
-            } else {
-                const float4 v = rawA_f[IN_U8 ? 0 : i];
-                split_tf32_fast(v.x, hi.x, lo.x);
-                split_tf32_fast(v.y, hi.y, lo.y);
-                split_tf32_fast(v.z, hi.z, lo.z);
-                split_tf32_fast(v.w, hi.w, lo.w);
+        for (int p = 0; p < MTC * NJ; ++p) {
+            if (p % NSLOT != wslot) continue;
+            const int mt = p / NJ, n0 = (p % NJ) * 16;
+            float v[16], v1[16], v2[16];
+            const uint32_t ta = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(mt * (Cfg::NACC * COUT) + n0);
+            tmem_ld16(ta, v);
+            tmem_ld16(ta + COUT, v1);
+            tmem_ld16(ta + 2 * COUT, v2);
+#pragma unroll
+            for (int x = 0; x < 16; ++x) v[x] += v1[x] + v2[x];
+            const int m = row0 + mt * 128 + lg * 32 + lane;
+            if (m < Cfg::M && !(dbg & 8)) {
+                float4* dst = reinterpret_cast<float4*>(out + (int64_t)m * COUT + n0);
+#pragma unroll
+                for (int x = 0; x < 16; x += 4)
+                    dst[x / 4] = make_float4(epi_s[n0 + x].apply(v[x]), epi_s[n0 + x + 1].apply(v[x + 1]),
+                                             epi_s[n0 + x + 2].apply(v[x + 2]), epi_s[n0 + x + 3].apply(v[x + 3]));
             }
-            *reinterpret_cast<float4*>(sA_hi + q * Cfg::A_PLANE + r * 16) = hi;
-            *reinterpret_cast<float4*>(sA_lo + q * Cfg::A_PLANE + r * 16) = lo;
-        }
-        // ---- stage B: member weights, transposed to [n][k] quads + hi/lo split ----
-#pragma unroll
-        for (int i = 0; i < B_PER_THREAD; ++i) {
-            const int u = tid + i * TC_THREADS;
-            if (u < B_UNITS) {
-                const int n = u % COUT, q = u / COUT;
-                float4 hi, lo;
-                split_tf32_fast(perturbed(rawB_t[i][0], s, rawB_n[i][0]), hi.x, lo.x);
-                split_tf32_fast(perturbed(rawB_t[i][1], s, rawB_n[i][1]), hi.y, lo.y);
-                split_tf32_fast(perturbed(rawB_t[i][2], s, rawB_n[i][2]), hi.z, lo.z);
-                split_tf32_fast(perturbed(rawB_t[i][3], s, rawB_n[i][3]), hi.w, lo.w);
-                *reinterpret_cast<float4*>(sB_hi + q * Cfg::B_PLANE + n * 16) = hi;
-                *reinterpret_cast<float4*>(sB_lo + q * Cfg::B_PLANE + n * 16) = lo;
-            }
-        }
-        if (c + 1 < Cfg::NCHUNK) load_chunk(c + 1);               // in flight across the fence / barrier / MMA issue
-        fence_proxy_async_smem();          // generic-proxy writes -> async proxy (tensor core reads)
-        __syncthreads();
-        if (tid == 0 && (dbg & 1)) mma_commit(&bars[st]);
-        if (tid == 0 && !(dbg & 1)) {
-            fence_after_thread_sync();
-            const uint32_t aH = smem_u32(sA_hi), aL = smem_u32(sA_lo), bH = smem_u32(sB_hi), bL = smem_u32(sB_lo);
-#pragma unroll
-            for (int mt = 0; mt < MTC; ++mt) {
-                const uint32_t d = tmem_base + mt * (Cfg::NACC * COUT);
-#pragma unroll
-                for (int k8 = 0; k8 < KC / 8; ++k8) {
-                    const uint32_t ao = 2 * k8 * Cfg::A_PLANE + mt * 128 * 16;
-                    const uint32_t bo = 2 * k8 * Cfg::B_PLANE;
-                    const uint64_t dAh = smem_desc(aH + ao, Cfg::A_PLANE, 128), dAl = smem_desc(aL + ao, Cfg::A_PLANE, 128);
-                    const uint64_t dBh = smem_desc(bH + bo, Cfg::B_PLANE, 128), dBl = smem_desc(bL + bo, Cfg::B_PLANE, 128);
-                    mma_tf32(d, dAh, dBh, IDESC, (c | k8) != 0);
-                    mma_tf32(d + COUT, dAl, dBh, IDESC, (c | k8) != 0);
-                    mma_tf32(d + 2 * COUT, dAh, dBl, IDESC, (c | k8) != 0);
-                }
-            }
-            mma_commit(&bars[st]);
-        }
-    }
-    // the last commit covers every MMA issued before it
-    {
-        constexpr int last = Cfg::NCHUNK - 1;
-        mbar_wait(&bars[last & 1], (last >> 1) & 1);
-    }
-    fence_after_thread_sync();
-
-    // ---- epilogue: TMEM -> registers -> bias (+BN) + activation -> NHWC global ----
-    float* out = out_base + slot * out_slot_stride + img * out_img_stride;
-    // warp w may only touch TMEM lanes 32*(w%4)..+31; the (M-tile, 16-column group) work items are dealt round-robin to
-    // the TC_THREADS/128 warps that share a lane group
-    const int lg = warp & 3, wslot = warp >> 2;
-    constexpr int NSLOT = TC_THREADS / 128, NJ = COUT / 16;
-#pragma unroll
-    for (int p = 0; p < MTC * NJ; ++p) {
-        if (p % NSLOT != wslot) continue;
-        const int mt = p / NJ, n0 = (p % NJ) * 16;
-        float v[16], v1[16], v2[16];
-        const uint32_t ta = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(mt * (Cfg::NACC * COUT) + n0);
-        tmem_ld16(ta, v);
-        tmem_ld16(ta + COUT, v1);
-        tmem_ld16(ta + 2 * COUT, v2);
-#pragma unroll
-        for (int x = 0; x < 16; ++x) v[x] += v1[x] + v2[x];      // small correction terms first
-        const int m = row0 + mt * 128 + lg * 32 + lane;
-        if (m < Cfg::M && !(dbg & 8)) {
-            float4* dst = reinterpret_cast<float4*>(out + (int64_t)m * COUT + n0);
-#pragma unroll
-            for (int x = 0; x < 16; x += 4)       // per-channel epilogue parameters come from shared memory
-                dst[x / 4] = make_float4(epi_s[n0 + x].apply(v[x]), epi_s[n0 + x + 1].apply(v[x + 1]),
-                                         epi_s[n0 + x + 2].apply(v[x + 2]), epi_s[n0 + x + 3].apply(v[x + 3]));
         }
     }
     fence_before_thread_sync();
@@ -271,7 +287,7 @@ static int launch_conv_tc(const SlotArgs& sa, const dne_layer_desc& L, const Lay
         attr_done = true;
     }
     dim3 grid((Cfg::M + Cfg::ROWS - 1) / Cfg::ROWS, n_slots, n_img);
-    kern<<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(sa, L.off_w, epi, in, in_slot_stride, in_img_stride, out,
+    kern<<<grid, TC_BLOCK, Cfg::SMEM_BYTES, st>>>(sa, L.off_w, epi, in, in_slot_stride, in_img_stride, out,
                                                    out_slot_stride, out_img_stride, g_dne_dbg);
     DNE_LAUNCHED(1);
     return 0;
