@@ -35,7 +35,7 @@ import numpy as np   # noqa: E402
 
 NET = "LargeModel"
 POP = 1000
-SLOTS = 256
+SLOTS = 512
 SIGMA, L2, LR = 0.005, 0.005, 0.01          # configurations/frostbite_es.json
 
 
@@ -143,15 +143,15 @@ def run_b200(args):
     # ------------------------------------------------------------------ value: device-resident generation
     lo, hi = shard.shard_bounds(n_pairs, rank, world)
     upd = ESUpdate(ctx, theta0, "adam", stepsize=LR)
-    # One slot table on one stream by default.  DNE_BENCH_STREAMS=2 splits the table over two streams (measured:
-    # +5% only -- the HBM-bound GEMV already fills every SM, so the halves time-slice instead of overlapping -- and it
-    # makes per-kernel event timings overlap, so the roofline leg keeps the single-stream schedule).
-    NS = int(os.environ.get("DNE_BENCH_STREAMS", "1"))
+    # Two slot tables of slots/2 on two streams by default: one table's conv chain (shared-memory / tensor bound)
+    # overlaps the other's HBM-bound noise GEMV (tools/sweep_overlap.py, r01: 512 slots: 1 table 594K, 2 tables 640K
+    # env-steps/s).  DNE_BENCH_STREAMS=1 gives the serial schedule; DNE_BENCH_PHASED=1 adds the phase-event hand-off.
+    NS = int(os.environ.get("DNE_BENCH_STREAMS", "2"))
     part = (args.slots // NS) // 2 * 2                          # whole antithetic pairs per table
     sfs = [SlotForward(ctx, net, part) for _ in range(NS)]
     streams = [torch.cuda.Stream(device=dev) for _ in range(NS)]
-    PHASED = os.environ.get("DNE_BENCH_PHASED", "1") == "1"
-    PHASE_MODE = int(os.environ.get("DNE_PHASE_MODE", "1" if NS > 2 else "0"))
+    PHASED = os.environ.get("DNE_BENCH_PHASED", "1" if NS > 2 else "0") == "1"
+    PHASE_MODE = int(os.environ.get("DNE_PHASE_MODE", "1"))
     phase_ev = [torch.cuda.Event() for _ in range(max(NS, 2))]
     for e in phase_ev:
         e.record()                                               # materialise the handles
@@ -285,6 +285,9 @@ def run_b200(args):
                 "traffic": traffic, "launches_timed": n_timed, "avg_launch_ms": avg_ms,
                 "algorithmic_bytes_per_launch": alg_bytes, "pairs_per_launch": pairs_per_launch,
                 "survey_bytes_per_launch": survey_bytes,
+                "schedule": f"{NS} slot table(s) on {NS} stream(s)" + ("; the timed GEMV launches overlap the other table's "
+                            "conv / tensor-core kernels, so avg_launch_ms includes that contention" if NS > 1 else ""),
+                "whole_run_frac": (args.steps * (hi - lo) * T * 4.0 * fc.cin * fc.cout / (ms_val * 1e-3) / 1e9 / peaks["hbm_gbs"]),
                 "frac_survey_bytes": (survey_bytes / (avg_ms * 1e-3) / 1e9 / peaks["hbm_gbs"]) if n_timed else None,
                 "note": "algorithmic bytes = one fc noise slice per antithetic PAIR (read once for both members); "
                         "survey_bytes = SURVEY 8d figure (4P + obs + action per env-step, every member its own slice). "

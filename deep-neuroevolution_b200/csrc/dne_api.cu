@@ -71,7 +71,6 @@ extern "C" int dne_ctx_destroy(dne_ctx* ctx) {
 extern "C" int dne_set_option(const char* name, int value) {
     DNE_CHECK_ARG(name, "name is null");
     if (strcmp(name, "conv_tc") == 0) { g_dne_conv_tc = value ? 1 : 0; return DNE_OK; }
-    if (strcmp(name, "dbg") == 0) { extern int g_dne_dbg; g_dne_dbg = value; return DNE_OK; }
     if (strcmp(name, "gemv_bulk") == 0) { g_dne_gemv_bulk = value ? 1 : 0; return DNE_OK; }
     if (strcmp(name, "gemv_ctas_per_sm") == 0 && value >= 1 && value <= 2) { g_dne_gemv_ctas_per_sm = value; return DNE_OK; }
     dne_set_error("dne_set_option: unknown option '%s'", name);

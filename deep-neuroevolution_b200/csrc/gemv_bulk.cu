@@ -129,12 +129,12 @@ gemv_bulk_kernel(SlotArgs sa, GemvSrc src, const float* __restrict__ X, int64_t 
 #pragma unroll
                 for (int j = 0; j <= GB_RPR; ++j) xm[g][j] = xs[g][r0 + rl0 + j];        // xs index = 1 + (row - 1)
             mbar_wait(&full_bar[s], (it / GB_STAGES) & 1);
-            const float4* rows4 = reinterpret_cast<const float4*>(stage_base + (size_t)s * (GB_STAGE_BYTES / 4)) +
-                                  (size_t)rl0 * NQ + t;
+            // explicit ld.shared (a C++ pointer into the re-aligned dynamic smem compiles to generic LD.E)
+            const uint32_t rows_a = tc05::smem_u32(stage_base) + s * GB_STAGE_BYTES + (rl0 * NQ + t) * 16;
             if (nr == RB) {
                 float4 v[GB_RPR];
 #pragma unroll
-                for (int j = 0; j < GB_RPR; ++j) v[j] = rows4[(size_t)j * NQ];
+                for (int j = 0; j < GB_RPR; ++j) v[j] = tc05::lds128(rows_a + j * NQ * 16);
 #pragma unroll
                 for (int j = 0; j < GB_RPR; ++j)
 #pragma unroll
@@ -159,7 +159,7 @@ gemv_bulk_kernel(SlotArgs sa, GemvSrc src, const float* __restrict__ X, int64_t 
             } else {
                 for (int j = 0; j < GB_RPR; ++j) {
                     if (rl0 + j < nr) {
-                        const float4 v = rows4[(size_t)j * NQ];
+                        const float4 v = tc05::lds128(rows_a + j * NQ * 16);
 #pragma unroll
                         for (int g = 0; g < G; ++g) {
                             acc[g][0] = fmaf(xm[g][j + 1], v.x, acc[g][0]);

@@ -67,6 +67,32 @@ __host__ __device__ constexpr uint32_t idesc_tf32(int M, int N) {
            | ((uint32_t)(M >> 4) << 24);  // m_dim
 }
 
+// Explicit shared-window accesses with 32-bit addresses.  Stores through a C++ pointer derived from the (re-aligned)
+// dynamic shared-memory base compile to GENERIC ST.E / LD.E (the cast hides the address space from ptxas).
+__device__ __forceinline__ void sts128(uint32_t saddr, const float4& v) {
+    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ float4 lds128(uint32_t saddr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
+    return v;
+}
+__device__ __forceinline__ float lds32(uint32_t saddr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(saddr));
+    return v;
+}
+
+// One lane of the (converged) warp is elected.  Issue pattern for tcgen05.mma / tcgen05.commit: the WHOLE warp runs the
+// loop and computes the descriptors (warp-uniform values -> uniform registers), and only the elected lane executes the
+// instruction.  Issuing from inside `if (lane == 0)` instead makes ptxas wrap every MMA in an ELECT/R2UR waterfall
+// loop (~15 instructions, ~100 cycles per MMA) -- measured in tools/probe_mma.py.
+__device__ __forceinline__ uint32_t elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+    return pred;
+}
+
 // D[tmem] (+)= A[smem] * B[smem]^T, issued by ONE thread
 __device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(

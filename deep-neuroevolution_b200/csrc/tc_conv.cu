@@ -17,10 +17,19 @@
 
 using namespace tc05;
 
-int g_dne_dbg = 0;                   // debug mask for conv_tc_kernel timing experiments (dne_set_option("dbg", mask))
-constexpr int TC_THREADS = 512;      // conv kernels: 16 staging warps ...
-constexpr int TC_BLOCK = TC_THREADS + 32;   // ... + one MMA-issuing warp (warp-specialised, mbarrier pipeline, no block barriers)
-constexpr int TG_THREADS = 256;      // theta GEMM / self-test
+#ifdef DNE_CONV_TRACE
+__device__ long long g_conv_trace[1024];
+#define TRACE(cond, i) do { if (TRACE_ON && (cond)) g_conv_trace[i] = clock64(); } while (0)
+extern "C" int dne_debug_conv_trace(long long* host_out) {
+    return cudaMemcpyFromSymbol(host_out, g_conv_trace, sizeof(g_conv_trace)) == cudaSuccess ? 0 : -3;
+}
+#else
+#define TRACE(cond, i) do { } while (0)
+#endif
+constexpr int TC_GROUPS = 4;                    // staging groups of 128 threads; group g owns smem stage g and stages chunks c = g (mod 4)
+constexpr int TC_THREADS = TC_GROUPS * 128;     // conv kernels: 16 staging warps ...
+constexpr int TC_BLOCK = TC_THREADS + 32;       // ... + one MMA-issuing warp (warp-specialised, mbarrier pipeline, no block barriers)
+constexpr int TG_THREADS = 256;                 // theta GEMM / self-test
 
 template <int CIN, int COUT, int KS, int STRIDE, int HIN, int HOUT, int PAD, bool IN_U8, int MTC, int KC>
 struct TcConvCfg {
@@ -32,23 +41,32 @@ struct TcConvCfg {
     static constexpr int B_PLANE = COUT * 16;                    // bytes per k-quad plane of B (= LBO of B)
     static constexpr int A_BYTES = (KC / 4) * A_PLANE;           // one of {hi, lo}
     static constexpr int B_BYTES = (KC / 4) * B_PLANE;
-    static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
-    static constexpr int NST = 3;                                // shared-memory stages (staging warps run ahead of the MMA warp)
-    static constexpr int PF = 2;                                 // chunks of raw global loads in flight per thread
+    // uint8 frames are staged as their integer value 0..255 -- exact in TF32, so A needs no lo plane (and one MMA less per
+    // k-step); the /255 of atari_wrappers.py:186 is applied to the accumulator in the epilogue
+    static constexpr int A_PLANES = IN_U8 ? 1 : 2;
+    static constexpr int STAGE_BYTES = A_PLANES * A_BYTES + 2 * B_BYTES;
+    static constexpr int NST = TC_GROUPS;                        // one shared-memory stage per staging group
     static constexpr int SMEM_BYTES = NST * STAGE_BYTES + 128;   // + alignment slack
-    // three independent accumulators per M tile (hi*hi, lo*hi, hi*lo): consecutive MMAs never wait on each other's
-    // result (a dependent accumulate chain of tiny N x K=8 MMAs is latency bound); summed in the epilogue
-    static constexpr int NACC = 3;
-    static constexpr int ACC_COLS = NACC * MTC * COUT;
+    static constexpr int ACC_COLS = MTC * COUT;
     static constexpr int TMEM_COLS = (ACC_COLS <= 32) ? 32 : (ACC_COLS <= 64) ? 64 : (ACC_COLS <= 128) ? 128 : (ACC_COLS <= 256) ? 256 : 512;
-    static_assert(K % KC == 0 && KC % 8 == 0 && CIN % 4 == 0 && COUT % 16 == 0, "tile constraints");
+    static constexpr int PASSES = ROWS / 32;                     // A rows per staging thread and chunk
+    static constexpr int B_UNITS = COUT * (KC / 4);
+    static constexpr int B_PER_THREAD = (B_UNITS + 127) / 128;
+    static_assert(KC == 16, "the lane -> (row, k-quad) staging map assumes 4 k-quads per chunk");
+    static_assert(K % KC == 0 && CIN % 4 == 0 && COUT % 16 == 0 && KS <= 8, "tile constraints");
+    static_assert(CIN == 4 || CIN % KC == 0, "a chunk is either 4 taps of 4 channels or part of one tap");
 };
+
+// Round-to-nearest TF32 hi part + fp32 remainder (the tensor core reads only the TF32 bits of lo): 3 instructions.
+__device__ __forceinline__ void split_tf32_rn(float x, float& hi, float& lo) {
+    hi = __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
+    lo = x - hi;
+}
 
 template <int CIN, int COUT, int KS, int STRIDE, int HIN, int HOUT, int PAD, bool IN_U8, int MTC, int KC>
 __global__ void __launch_bounds__(TC_BLOCK, 2)
 conv_tc_kernel(SlotArgs sa, int64_t off_w, LayerEpi epi, const void* __restrict__ in_base, int64_t in_slot_stride,
-               int64_t in_img_stride, float* __restrict__ out_base, int64_t out_slot_stride, int64_t out_img_stride,
-               int dbg) {
+               int64_t in_img_stride, float* __restrict__ out_base, int64_t out_slot_stride, int64_t out_img_stride) {
     using Cfg = TcConvCfg<CIN, COUT, KS, STRIDE, HIN, HOUT, PAD, IN_U8, MTC, KC>;
     const int slot = blockIdx.y;
     if (!slot_active(sa, slot)) return;
@@ -57,13 +75,17 @@ conv_tc_kernel(SlotArgs sa, int64_t off_w, LayerEpi epi, const void* __restrict_
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     constexpr int NST = Cfg::NST;
     constexpr int STAGE_WARPS = TC_THREADS / 32;
+    const bool TRACE_ON = CIN == 32 && COUT == 64 && blockIdx.x == 0 && blockIdx.y == 7;
+    TRACE(tid == 0, 0);
+#ifdef DNE_CONV_TRACE
+    if (TRACE_ON && tid == 0) { unsigned long long ns; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(ns)); g_conv_trace[4] = (long long)ns; }
+#endif
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
     __shared__ uint64_t full_bar[NST], empty_bar[NST], done_bar;
     __shared__ uint32_t tmem_base_s;
     __shared__ ChanEpi epi_s[COUT];                              // per-channel epilogue parameters, built once per CTA
-    __shared__ float2 u8_lut[IN_U8 ? 256 : 1];                   // uint8 -> (hi, lo) of value/255 (atari_wrappers.py:186)
 
     const float* th = slot_theta(sa, slot);
     const int64_t idx = sa.noise_idx[slot];
@@ -72,19 +94,13 @@ conv_tc_kernel(SlotArgs sa, int64_t off_w, LayerEpi epi, const void* __restrict_
     if (warp == 0) tmem_alloc(&tmem_base_s, Cfg::TMEM_COLS);
     if (tid == 32) {
         for (int i = 0; i < NST; ++i) {
-            mbar_init(&full_bar[i], STAGE_WARPS);                // one arrival per staging warp
+            mbar_init(&full_bar[i], 4);                          // one arrival per warp of the owning staging group
             mbar_init(&empty_bar[i], 1);                         // tcgen05.commit of the MMA warp
         }
         mbar_init(&done_bar, 1);
         fence_mbar_init();
     }
     if (tid < COUT) epi_s[tid] = make_chan_epi(sa, epi, slot, COUT, tid, th, idx, s);
-    if (IN_U8 && tid >= 256 && tid < 512) {
-        const float v = __fdiv_rn((float)(tid - 256), 255.0f);
-        float hi, lo;
-        split_tf32_fast(v, hi, lo);
-        u8_lut[IN_U8 ? tid - 256 : 0] = make_float2(hi, lo);
-    }
     fence_before_thread_sync();
     __syncthreads();
     fence_after_thread_sync();
@@ -92,36 +108,38 @@ conv_tc_kernel(SlotArgs sa, int64_t off_w, LayerEpi epi, const void* __restrict_
     constexpr uint32_t IDESC = idesc_tf32(128, COUT);
 
     if (warp == STAGE_WARPS) {
-        // =========================== MMA warp: one lane feeds the tensor core ===========================
-        if (lane == 0) {
-            for (int c = 0; c < Cfg::NCHUNK; ++c) {
-                const int st = c % NST;
-                mbar_wait(&full_bar[st], (c / NST) & 1);         // the staging warps have filled (and fenced) this stage
-                fence_after_thread_sync();
-                if (!(dbg & 1)) {
-                    const uint32_t aH = smem_u32(smem + st * Cfg::STAGE_BYTES), aL = aH + Cfg::A_BYTES,
-                                   bH = aL + Cfg::A_BYTES, bL = bH + Cfg::B_BYTES;
+        // ============ MMA warp: converged loop, descriptors in uniform registers, one elected lane issues ============
+        const uint32_t s0 = smem_u32(smem);
+        const uint64_t dA0 = smem_desc(s0, Cfg::A_PLANE, 128);
+        const uint64_t dB0 = smem_desc(s0 + Cfg::A_PLANES * Cfg::A_BYTES, Cfg::B_PLANE, 128);
+        for (int c = 0; c < Cfg::NCHUNK; ++c) {
+            const int st = c % NST;
+            mbar_wait(&full_bar[st], (c / NST) & 1);             // the staging group has filled (and fenced) this stage
+            fence_after_thread_sync();
+            TRACE(lane == 0, 16 + 2 * c);
+            const uint64_t so = (uint64_t)((st * Cfg::STAGE_BYTES) >> 4);    // descriptor address field is in 16-byte units
+            if (elect_one()) {
 #pragma unroll
-                    for (int mt = 0; mt < MTC; ++mt) {
-                        const uint32_t d = tmem_base + mt * (Cfg::NACC * COUT);
+                for (int mt = 0; mt < MTC; ++mt) {
+                    const uint32_t d = tmem_base + mt * COUT;
 #pragma unroll
-                        for (int k8 = 0; k8 < KC / 8; ++k8) {
-                            const uint32_t ao = 2 * k8 * Cfg::A_PLANE + mt * 128 * 16;
-                            const uint32_t bo = 2 * k8 * Cfg::B_PLANE;
-                            const uint64_t dAh = smem_desc(aH + ao, Cfg::A_PLANE, 128), dAl = smem_desc(aL + ao, Cfg::A_PLANE, 128);
-                            const uint64_t dBh = smem_desc(bH + bo, Cfg::B_PLANE, 128), dBl = smem_desc(bL + bo, Cfg::B_PLANE, 128);
-                            mma_tf32(d, dAh, dBh, IDESC, (c | k8) != 0);
-                            mma_tf32(d + COUT, dAl, dBh, IDESC, (c | k8) != 0);
-                            mma_tf32(d + 2 * COUT, dAh, dBl, IDESC, (c | k8) != 0);
-                        }
+                    for (int k8 = 0; k8 < KC / 8; ++k8) {
+                        const uint64_t dAh = dA0 + so + (uint64_t)((2 * k8 * Cfg::A_PLANE + mt * 128 * 16) >> 4);
+                        const uint64_t dBh = dB0 + so + (uint64_t)((2 * k8 * Cfg::B_PLANE) >> 4);
+                        mma_tf32(d, dAh, dBh, IDESC, (c | k8) != 0);
+                        if (!IN_U8) mma_tf32(d, dAh + (uint64_t)(Cfg::A_BYTES >> 4), dBh, IDESC, 1);
+                        mma_tf32(d, dAh, dBh + (uint64_t)(Cfg::B_BYTES >> 4), IDESC, 1);
                     }
                 }
                 mma_commit(&empty_bar[st]);                      // stage reusable once these MMAs have read it
+                if (c == Cfg::NCHUNK - 1) mma_commit(&done_bar); // every MMA of the tile has completed
             }
-            mma_commit(&done_bar);                               // every MMA of the tile has completed
+            __syncwarp();
+            TRACE(lane == 0, 17 + 2 * c);
         }
     } else {
-        // =========================== staging warps: perturb + im2col -> shared memory =====================
+        // ============== staging groups: perturb + im2col -> shared memory (group g <-> stage g) ==============
+        const int g = warp >> 2, wg = warp & 3, tg = tid & 127;
         const float* nz = sa.noise + idx + off_w;
         const float* tw = th + off_w;
         const uint8_t* in_u8 = nullptr;
@@ -129,146 +147,138 @@ conv_tc_kernel(SlotArgs sa, int64_t off_w, LayerEpi epi, const void* __restrict_
         if (IN_U8) in_u8 = (const uint8_t*)in_base + slot * in_slot_stride + img * in_img_stride;
         else in_f = (const float*)in_base + slot * in_slot_stride + img * in_img_stride;
 
-        // A staging units of this thread: (row r, k-quad q), r fastest; r is fixed per unit index across chunks
-        constexpr int A_UNITS = Cfg::ROWS * (KC / 4);
-        constexpr int A_PER_THREAD = A_UNITS / TC_THREADS;
-        static_assert(A_UNITS % TC_THREADS == 0 && (Cfg::ROWS % TC_THREADS == 0 || TC_THREADS % Cfg::ROWS == 0), "A staging map");
-        int a_iy0[A_PER_THREAD], a_ix0[A_PER_THREAD];
-        bool a_ok[A_PER_THREAD];
+        // A: in every chunk this thread stages k-quad q of the rows i*32 + wg*8 + (lane & 7); a quarter warp covers 8
+        // consecutive rows of one quad plane (128 contiguous shared-memory bytes: conflict-free 16-byte stores) and the
+        // 4 quads of one row are 4 lanes reading 64 contiguous bytes (float) / 16 bytes (uint8) of the input
+        constexpr int PASSES = Cfg::PASSES;
+        const int q = lane >> 3;
+        int a_off[PASSES];               // input element offset of the row's (ky = 0, kx = 0, ci = 0) corner
+        uint32_t a_vm[PASSES];           // validity: bit ky -> row iy0+ky inside the image, bit 8+kx -> column ix0+kx inside
 #pragma unroll
-        for (int i = 0; i < A_PER_THREAD; ++i) {
-            const int u = tid + i * TC_THREADS;
-            const int m = row0 + (u % Cfg::ROWS);
-            a_ok[i] = m < Cfg::M;
-            a_iy0[i] = (m / HOUT) * STRIDE - PAD;
-            a_ix0[i] = (m % HOUT) * STRIDE - PAD;
+        for (int i = 0; i < PASSES; ++i) {
+            const int m = row0 + i * 32 + wg * 8 + (lane & 7);
+            const int mc = min(m, Cfg::M - 1);
+            const int oy = mc / HOUT, ox = mc - oy * HOUT;
+            const int iy0 = oy * STRIDE - PAD, ix0 = ox * STRIDE - PAD;
+            a_off[i] = (iy0 * HIN + ix0) * CIN;
+            const int ylo = max(0, -iy0), yhi = min(KS, HIN - iy0), xlo = max(0, -ix0), xhi = min(KS, HIN - ix0);
+            const uint32_t my = (1u << yhi) - (1u << ylo), mx = (1u << xhi) - (1u << xlo);
+            a_vm[i] = (m < Cfg::M) ? (my | (mx << 8)) : 0u;
         }
-        constexpr int B_UNITS = COUT * (KC / 4);
-        constexpr int B_PER_THREAD = (B_UNITS + TC_THREADS - 1) / TC_THREADS;
+        // B: unit u = tg + i*128 -> (column n = u % COUT, k-quad u / COUT); element offset of its first k row
+        constexpr int BPT = Cfg::B_PER_THREAD;
+        int b_off[BPT];
+#pragma unroll
+        for (int i = 0; i < BPT; ++i) {
+            const int u = tg + i * 128;
+            b_off[i] = 4 * (u / COUT) * COUT + (u % COUT);
+        }
+        const uint32_t sA_hi = smem_u32(smem) + g * Cfg::STAGE_BYTES + q * Cfg::A_PLANE + (wg * 8 + (lane & 7)) * 16;   // + i*512 per pass
+        const uint32_t sA_lo = sA_hi + Cfg::A_BYTES;
+        const uint32_t sB_hi = smem_u32(smem) + g * Cfg::STAGE_BYTES + Cfg::A_PLANES * Cfg::A_BYTES + tg * 16;         // + i*2048 per unit
+        const uint32_t sB_lo = sB_hi + Cfg::B_BYTES;
 
-        // Register software pipeline: the raw global loads of chunk c+PF are in flight while chunk c is converted
-        constexpr int PF = Cfg::PF;
-        uint32_t rawA_u8[PF][IN_U8 ? A_PER_THREAD : 1];
-        float4 rawA_f[PF][IN_U8 ? 1 : A_PER_THREAD];
-        float rawB_t[PF][B_PER_THREAD][4], rawB_n[PF][B_PER_THREAD][4];
-        auto load_chunk = [&](int c, int slot_) {
-            const int k0 = c * KC;
+        for (int c = g, it = 0; c < Cfg::NCHUNK; c += TC_GROUPS, ++it) {
+            // ---- raw global loads of the chunk (issued before the stage wait so that their latency overlaps it) ----
+            TRACE(tg == 0, 128 + (g * 16 + it) * 4 + 0);
+            const int k = c * KC + 4 * q;
+            const int ci = k % CIN, t = k / CIN;
+            const int ky = t / KS, kx = t - ky * KS;
+            const int tap = (ky * HIN + kx) * CIN + ci;
+            const uint32_t vbit = (1u << ky) | (1u << (8 + kx));
+            uint32_t rawA_u8[IN_U8 ? PASSES : 1];
+            float4 rawA_f[IN_U8 ? 1 : PASSES];
 #pragma unroll
-            for (int i = 0; i < A_PER_THREAD; ++i) {
-                const int u = tid + i * TC_THREADS;
-                const int q = u / Cfg::ROWS;
-                const int k = k0 + 4 * q;
-                const int ci = k % CIN, t = k / CIN;
-                const int kx = t % KS, ky = t / KS;
-                const int iy = a_iy0[i] + ky, ix = a_ix0[i] + kx;
-                const bool ok = a_ok[i] && iy >= 0 && iy < HIN && ix >= 0 && ix < HIN && !(dbg & 2);
-                const int e = (iy * HIN + ix) * CIN + ci;
-                if (IN_U8) rawA_u8[slot_][IN_U8 ? i : 0] = ok ? *reinterpret_cast<const uint32_t*>(in_u8 + e) : 0u;
-                else rawA_f[slot_][IN_U8 ? 0 : i] = ok ? *reinterpret_cast<const float4*>(in_f + e) : make_float4(0.f, 0.f, 0.f, 0.f);
+            for (int i = 0; i < PASSES; ++i) {
+                const bool ok = (a_vm[i] & vbit) == vbit;
+                if (IN_U8) rawA_u8[IN_U8 ? i : 0] = ok ? *reinterpret_cast<const uint32_t*>(in_u8 + a_off[i] + tap) : 0u;
+                else rawA_f[IN_U8 ? 0 : i] = ok ? *reinterpret_cast<const float4*>(in_f + a_off[i] + tap) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
+            float rawB_t[BPT][4], rawB_n[BPT][4];
+            const int64_t fb = (int64_t)c * KC * COUT;
 #pragma unroll
-            for (int i = 0; i < B_PER_THREAD; ++i) {
-                const int u = tid + i * TC_THREADS;
-                if (u < B_UNITS && !(dbg & 4)) {
-                    const int n = u % COUT, q = u / COUT;
-                    const int64_t f = (int64_t)(k0 + 4 * q) * COUT + n;
+            for (int i = 0; i < BPT; ++i) {
+                if (tg + i * 128 < Cfg::B_UNITS) {
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
-                        rawB_t[slot_][i][j] = tw[f + j * COUT];
-                        rawB_n[slot_][i][j] = nz[f + j * COUT];
+                        rawB_t[i][j] = tw[fb + b_off[i] + j * COUT];
+                        rawB_n[i][j] = nz[fb + b_off[i] + j * COUT];
                     }
                 }
             }
-        };
+            mbar_wait(&empty_bar[g], (it & 1) ^ 1);              // the MMAs of this group's previous chunk have drained the stage
+            TRACE(tg == 0, 128 + (g * 16 + it) * 4 + 1);
+            // ---- convert + store: A ----
 #pragma unroll
-        for (int p = 0; p < PF; ++p)
-            if (p < Cfg::NCHUNK) load_chunk(p, p);
-
-        // the chunk loop is unrolled by PF so that the register ring is indexed statically
-        for (int c0 = 0; c0 < Cfg::NCHUNK; c0 += PF) {
-#pragma unroll
-            for (int p = 0; p < PF; ++p) {
-                const int c = c0 + p;
-                if (c < Cfg::NCHUNK) {
-                    const int st = c % NST;
-                    mbar_wait(&empty_bar[st], ((c / NST) & 1) ^ 1);      // MMAs of chunk c-NST have drained this stage
-                    uint8_t* sA_hi = smem + st * Cfg::STAGE_BYTES;
-                    uint8_t* sA_lo = sA_hi + Cfg::A_BYTES;
-                    uint8_t* sB_hi = sA_lo + Cfg::A_BYTES;
-                    uint8_t* sB_lo = sB_hi + Cfg::B_BYTES;
-#pragma unroll
-                    for (int i = 0; i < A_PER_THREAD; ++i) {
-                        const int u = tid + i * TC_THREADS;
-                        const int r = u % Cfg::ROWS, q = u / Cfg::ROWS;
-                        float4 hi, lo;
-                        if (IN_U8) {
-                            const uint32_t px = rawA_u8[p][IN_U8 ? i : 0];
-                            const float2 e0 = u8_lut[px & 255u], e1 = u8_lut[(px >> 8) & 255u],
-                                         e2 = u8_lut[(px >> 16) & 255u], e3 = u8_lut[IN_U8 ? (px >> 24) : 0];
-                            hi = make_float4(e0.x, e1.x, e2.x, e3.x);
-                            lo = make_float4(e0.y, e1.y, e2.y, e3.y);
-                        } else {
-                            const float4 v = rawA_f[p][IN_U8 ? 0 : i];
-                            split_tf32_fast(v.x, hi.x, lo.x);
-                            split_tf32_fast(v.y, hi.y, lo.y);
-                            split_tf32_fast(v.z, hi.z, lo.z);
-                            split_tf32_fast(v.w, hi.w, lo.w);
-                        }
-                        *reinterpret_cast<float4*>(sA_hi + q * Cfg::A_PLANE + r * 16) = hi;
-                        *reinterpret_cast<float4*>(sA_lo + q * Cfg::A_PLANE + r * 16) = lo;
-                    }
-#pragma unroll
-                    for (int i = 0; i < B_PER_THREAD; ++i) {
-                        const int u = tid + i * TC_THREADS;
-                        if (u < B_UNITS) {
-                            const int n = u % COUT, q = u / COUT;
-                            float4 hi, lo;
-                            split_tf32_fast(perturbed(rawB_t[p][i][0], s, rawB_n[p][i][0]), hi.x, lo.x);
-                            split_tf32_fast(perturbed(rawB_t[p][i][1], s, rawB_n[p][i][1]), hi.y, lo.y);
-                            split_tf32_fast(perturbed(rawB_t[p][i][2], s, rawB_n[p][i][2]), hi.z, lo.z);
-                            split_tf32_fast(perturbed(rawB_t[p][i][3], s, rawB_n[p][i][3]), hi.w, lo.w);
-                            *reinterpret_cast<float4*>(sB_hi + q * Cfg::B_PLANE + n * 16) = hi;
-                            *reinterpret_cast<float4*>(sB_lo + q * Cfg::B_PLANE + n * 16) = lo;
-                        }
-                    }
-                    if (c + PF < Cfg::NCHUNK) load_chunk(c + PF, p);     // refill this ring slot
-                    fence_proxy_async_smem();                            // generic-proxy writes -> async proxy
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&full_bar[st]);
+            for (int i = 0; i < PASSES; ++i) {
+                if (IN_U8) {
+                    const uint32_t px = rawA_u8[IN_U8 ? i : 0];
+                    sts128(sA_hi + i * 512, make_float4((float)(px & 255u), (float)((px >> 8) & 255u), (float)((px >> 16) & 255u),
+                                                        (float)(px >> 24)));
+                } else {
+                    const float4 v = rawA_f[IN_U8 ? 0 : i];
+                    float4 hi, lo;
+                    split_tf32_rn(v.x, hi.x, lo.x);
+                    split_tf32_rn(v.y, hi.y, lo.y);
+                    split_tf32_rn(v.z, hi.z, lo.z);
+                    split_tf32_rn(v.w, hi.w, lo.w);
+                    sts128(sA_hi + i * 512, hi);
+                    sts128(sA_lo + i * 512, lo);
                 }
             }
+            TRACE(tg == 0, 128 + (g * 16 + it) * 4 + 2);
+            // ---- perturb + convert + store: B ----
+#pragma unroll
+            for (int i = 0; i < BPT; ++i) {
+                const int u = tg + i * 128;
+                if (u < Cfg::B_UNITS) {
+                    float4 hi, lo;
+                    split_tf32_rn(perturbed(rawB_t[i][0], s, rawB_n[i][0]), hi.x, lo.x);
+                    split_tf32_rn(perturbed(rawB_t[i][1], s, rawB_n[i][1]), hi.y, lo.y);
+                    split_tf32_rn(perturbed(rawB_t[i][2], s, rawB_n[i][2]), hi.z, lo.z);
+                    split_tf32_rn(perturbed(rawB_t[i][3], s, rawB_n[i][3]), hi.w, lo.w);
+                    sts128(sB_hi + i * 2048, hi);                    // unit u at u*16 == (u / COUT) * B_PLANE + (u % COUT) * 16
+                    sts128(sB_lo + i * 2048, lo);
+                }
+            }
+            fence_proxy_async_smem();                            // generic-proxy writes -> async proxy
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&full_bar[g]);
+            TRACE(tg == 0, 128 + (g * 16 + it) * 4 + 3);
         }
-        // ---- epilogue: TMEM -> registers -> bias (+BN) + activation -> NHWC global ----
+        // ---- epilogue: TMEM -> registers -> (/255) + bias (+BN) + activation -> NHWC global ----
         mbar_wait(&done_bar, 0);
         fence_after_thread_sync();
+        TRACE(tid == 0, 2);
         float* out = out_base + slot * out_slot_stride + img * out_img_stride;
         // warp w may only touch TMEM lanes 32*(w%4)..+31; the (M-tile, 16-column group) work items are dealt round-robin
-        // to the TC_THREADS/128 warps that share a lane group
-        const int lg = warp & 3, wslot = warp >> 2;
-        constexpr int NSLOT = TC_THREADS / 128, NJ = COUT / 16;
+        // to the TC_GROUPS warps that share a lane group
+        constexpr int NJ = COUT / 16;
+        constexpr float IN_SCALE = IN_U8 ? (1.0f / 255.0f) : 1.0f;
 #pragma unroll
         for (int p = 0; p < MTC * NJ; ++p) {
-            if (p % NSLOT != wslot) continue;
+            if (p % TC_GROUPS != g) continue;
             const int mt = p / NJ, n0 = (p % NJ) * 16;
-            float v[16], v1[16], v2[16];
-            const uint32_t ta = tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(mt * (Cfg::NACC * COUT) + n0);
-            tmem_ld16(ta, v);
-            tmem_ld16(ta + COUT, v1);
-            tmem_ld16(ta + 2 * COUT, v2);
-#pragma unroll
-            for (int x = 0; x < 16; ++x) v[x] += v1[x] + v2[x];
-            const int m = row0 + mt * 128 + lg * 32 + lane;
-            if (m < Cfg::M && !(dbg & 8)) {
+            float v[16];
+            tmem_ld16(tmem_base + ((uint32_t)(wg * 32) << 16) + (uint32_t)(mt * COUT + n0), v);
+            const int m = row0 + mt * 128 + wg * 32 + lane;
+            if (m < Cfg::M) {
                 float4* dst = reinterpret_cast<float4*>(out + (int64_t)m * COUT + n0);
 #pragma unroll
-                for (int x = 0; x < 16; x += 4)
+                for (int x = 0; x < 16; x += 4) {
+                    if (IN_U8) { v[x] *= IN_SCALE; v[x + 1] *= IN_SCALE; v[x + 2] *= IN_SCALE; v[x + 3] *= IN_SCALE; }
                     dst[x / 4] = make_float4(epi_s[n0 + x].apply(v[x]), epi_s[n0 + x + 1].apply(v[x + 1]),
                                              epi_s[n0 + x + 2].apply(v[x + 2]), epi_s[n0 + x + 3].apply(v[x + 3]));
+                }
             }
         }
     }
     fence_before_thread_sync();
     __syncthreads();
+    TRACE(tid == 0, 3);
+#ifdef DNE_CONV_TRACE
+    if (TRACE_ON && tid == 0) { unsigned long long ns; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(ns)); g_conv_trace[5] = (long long)ns; }
+#endif
     if (warp == 0) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
 }
 
@@ -288,7 +298,7 @@ static int launch_conv_tc(const SlotArgs& sa, const dne_layer_desc& L, const Lay
     }
     dim3 grid((Cfg::M + Cfg::ROWS - 1) / Cfg::ROWS, n_slots, n_img);
     kern<<<grid, TC_BLOCK, Cfg::SMEM_BYTES, st>>>(sa, L.off_w, epi, in, in_slot_stride, in_img_stride, out,
-                                                   out_slot_stride, out_img_stride, g_dne_dbg);
+                                                   out_slot_stride, out_img_stride);
     DNE_LAUNCHED(1);
     return 0;
 }
@@ -462,10 +472,8 @@ theta_gemm_tc_kernel(const float* __restrict__ X, int M, int K, int N, const flo
     for (int c = 0; c < nchunk; ++c) {
         const int st = c & 1;
         if (c >= 2) mbar_wait(&bars[st], ((c >> 1) - 1) & 1);
-        uint8_t* sA_hi = smem + st * TG_STAGE_BYTES;
-        uint8_t* sA_lo = sA_hi + TG_A_BYTES;
-        uint8_t* sB_hi = sA_lo + TG_A_BYTES;
-        uint8_t* sB_lo = sB_hi + TG_B_BYTES;
+        const uint32_t sA_hi = smem_u32(smem) + st * TG_STAGE_BYTES, sA_lo = sA_hi + TG_A_BYTES, sB_hi = sA_lo + TG_A_BYTES,
+                       sB_lo = sB_hi + TG_B_BYTES;
 #pragma unroll
         for (int i = 0; i < 2; ++i) {
             const int u = tid + i * TG_THREADS;
@@ -474,32 +482,33 @@ theta_gemm_tc_kernel(const float* __restrict__ X, int M, int K, int N, const flo
             split_tf32_fast(rawA[i].y, hi.y, lo.y);
             split_tf32_fast(rawA[i].z, hi.z, lo.z);
             split_tf32_fast(rawA[i].w, hi.w, lo.w);
-            *reinterpret_cast<float4*>(sA_hi + (u / TG_BM) * TG_A_PLANE + (u % TG_BM) * 16) = hi;
-            *reinterpret_cast<float4*>(sA_lo + (u / TG_BM) * TG_A_PLANE + (u % TG_BM) * 16) = lo;
+            sts128(sA_hi + u * 16, hi);                          // (u / TG_BM) * TG_A_PLANE + (u % TG_BM) * 16 == u * 16
+            sts128(sA_lo + u * 16, lo);
             split_tf32_fast(rawB[i][0], hi.x, lo.x);
             split_tf32_fast(rawB[i][1], hi.y, lo.y);
             split_tf32_fast(rawB[i][2], hi.z, lo.z);
             split_tf32_fast(rawB[i][3], hi.w, lo.w);
-            *reinterpret_cast<float4*>(sB_hi + (u / TG_BN) * TG_B_PLANE + (u % TG_BN) * 16) = hi;
-            *reinterpret_cast<float4*>(sB_lo + (u / TG_BN) * TG_B_PLANE + (u % TG_BN) * 16) = lo;
+            sts128(sB_hi + u * 16, hi);
+            sts128(sB_lo + u * 16, lo);
         }
         if (c + 1 < nchunk) load_chunk(c + 1);
         fence_proxy_async_smem();
         __syncthreads();
-        if (tid == 0) {
+        if (warp == 0) {                                         // converged warp, one elected lane issues (tc05.cuh: elect_one)
             fence_after_thread_sync();
-            const uint32_t aH = smem_u32(sA_hi), aL = smem_u32(sA_lo), bH = smem_u32(sB_hi), bL = smem_u32(sB_lo);
+            const uint64_t dA = smem_desc(smem_u32(smem) + st * TG_STAGE_BYTES, TG_A_PLANE, 128);
+            const uint64_t dB = smem_desc(smem_u32(smem) + st * TG_STAGE_BYTES + 2 * TG_A_BYTES, TG_B_PLANE, 128);
+            if (elect_one()) {
 #pragma unroll
-            for (int k8 = 0; k8 < TG_KC / 8; ++k8) {
-                const uint64_t dAh = smem_desc(aH + 2 * k8 * TG_A_PLANE, TG_A_PLANE, 128);
-                const uint64_t dAl = smem_desc(aL + 2 * k8 * TG_A_PLANE, TG_A_PLANE, 128);
-                const uint64_t dBh = smem_desc(bH + 2 * k8 * TG_B_PLANE, TG_B_PLANE, 128);
-                const uint64_t dBl = smem_desc(bL + 2 * k8 * TG_B_PLANE, TG_B_PLANE, 128);
-                mma_tf32(tmem_base, dAh, dBh, IDESC, (c | k8) != 0);
-                mma_tf32(tmem_base, dAl, dBh, IDESC, 1);
-                mma_tf32(tmem_base, dAh, dBl, IDESC, 1);
+                for (int k8 = 0; k8 < TG_KC / 8; ++k8) {
+                    const uint64_t dAh = dA + (uint64_t)((2 * k8 * TG_A_PLANE) >> 4), dBh = dB + (uint64_t)((2 * k8 * TG_B_PLANE) >> 4);
+                    mma_tf32(tmem_base, dAh, dBh, IDESC, (c | k8) != 0);
+                    mma_tf32(tmem_base, dAh + (uint64_t)(TG_A_BYTES >> 4), dBh, IDESC, 1);
+                    mma_tf32(tmem_base, dAh, dBh + (uint64_t)(TG_B_BYTES >> 4), IDESC, 1);
+                }
+                mma_commit(&bars[st]);
             }
-            mma_commit(&bars[st]);
+            __syncwarp();
         }
     }
     if (nchunk > 0) mbar_wait(&bars[(nchunk - 1) & 1], ((nchunk - 1) >> 1) & 1);

@@ -57,30 +57,85 @@ __global__ void __launch_bounds__(128) tc_probe_kernel(const float* __restrict__
     fence_after_thread_sync();
     const uint32_t tmem_base = tmem_base_s;
     constexpr uint32_t IDESC = idesc_tf32(128, N);
-    if (tid == 0) {
-        const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB);
-        const long long t0 = clock64();
-        for (int rep = 0; rep < reps; ++rep) {
+    __shared__ uint64_t full_b, empty_b;
+    __shared__ int stop_flag;
+    if (tid == 0) { mbar_init(&full_b, 1); mbar_init(&empty_b, 1); fence_mbar_init(); stop_flag = 0; }
+    __syncthreads();
+    const int mode = layout >> 4;           // 0 chain, 1 commit+wait per 6 MMAs, 2 chain + generic-store traffic,
+    layout &= 15;                           // 3 chain + st.shared traffic, 4 full/empty ping-pong with a staging warp
+    // converged-warp issue (tc05.cuh: elect_one): descriptors are warp-uniform, one elected lane issues
+    const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB);
+    uint64_t dA[4], dB[4];
 #pragma unroll
-            for (int k8 = 0; k8 < 4; ++k8) {
-                uint64_t dA, dB;
-                if (layout == 0) {
-                    dA = desc_layout(a0 + 2 * k8 * 128 * 16, 128 * 16, 128, 0);
-                    dB = desc_layout(b0 + 2 * k8 * N * 16, N * 16, 128, 0);
-                } else if (layout == 1) {
-                    dA = desc_layout(a0 + k8 * 128 * 32, 16, 256, 6);
-                    dB = desc_layout(b0 + k8 * N * 32, 16, 256, 6);
-                } else {
-                    dA = desc_layout(a0 + k8 * 32, 16, 1024, 2);
-                    dB = desc_layout(b0 + k8 * 32, 16, 1024, 2);
-                }
-                mma_tf32(tmem_base, dA, dB, IDESC, (rep | k8) != 0);
+    for (int k8 = 0; k8 < 4; ++k8) {
+        if (layout == 0) {
+            dA[k8] = desc_layout(a0 + 2 * k8 * 128 * 16, 128 * 16, 128, 0);
+            dB[k8] = desc_layout(b0 + 2 * k8 * N * 16, N * 16, 128, 0);
+        } else if (layout == 1) {
+            dA[k8] = desc_layout(a0 + k8 * 128 * 32, 16, 256, 6);
+            dB[k8] = desc_layout(b0 + k8 * N * 32, 16, 256, 6);
+        } else {
+            dA[k8] = desc_layout(a0 + k8 * 32, 16, 1024, 2);
+            dB[k8] = desc_layout(b0 + k8 * 32, 16, 1024, 2);
+        }
+    }
+    auto issue = [&](int n_mma, bool first) {          // n_mma is 4 or 6 (compile-time at the call sites)
+        if (elect_one()) {
+#pragma unroll
+            for (int i = 0; i < 6; ++i)
+                if (i < n_mma) mma_tf32(tmem_base, dA[i & 3], dB[i & 3], IDESC, !(first && i == 0));
+        }
+        __syncwarp();
+    };
+    uint8_t* scratch = sB + 16384;          // 16 KB scratch for the store-traffic modes
+    if (warp == 0) {
+        const long long t0 = clock64();
+        if (mode == 0 || mode == 2 || mode == 3) {
+            for (int rep = 0; rep < reps; ++rep) issue(4, rep == 0);
+            if (elect_one()) mma_commit(&bar);
+            __syncwarp();
+            mbar_wait(&bar, 0);
+        } else if (mode == 1) {
+            for (int rep = 0; rep < reps; ++rep) {
+                issue(6, rep == 0);
+                if (elect_one()) mma_commit(&bar);
+                __syncwarp();
+                mbar_wait(&bar, rep & 1);
+            }
+        } else {
+            for (int rep = 0; rep < reps; ++rep) {
+                mbar_wait(&full_b, rep & 1);
+                fence_after_thread_sync();
+                issue(6, rep == 0);
+                if (elect_one()) mma_commit(&empty_b);
+                __syncwarp();
+            }
+            if (elect_one()) mma_commit(&bar);
+            __syncwarp();
+            mbar_wait(&bar, 0);
+        }
+        const long long t1 = clock64();
+        if (lane == 0) { cycles[0] = t1 - t0; *(volatile int*)&stop_flag = 1; }
+    } else if (warp >= 1 && (mode == 2 || mode == 3)) {
+        const float4 v = make_float4(1.f, 2.f, 3.f, 4.f);
+        uint8_t* p = scratch + (tid - 32) * 16;
+        const uint32_t pa = smem_u32(p);
+        int guard = 0;
+        while (*(volatile int*)&stop_flag == 0 && ++guard < (1 << 22)) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                if (mode == 2) asm volatile("st.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p + j * 1536), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+                else asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(pa + j * 1536), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
             }
         }
-        mma_commit(&bar);
-        mbar_wait(&bar, 0);
-        const long long t1 = clock64();
-        cycles[0] = t1 - t0;
+    } else if (warp == 1 && mode == 4) {
+        for (int rep = 0; rep < reps; ++rep) {
+            mbar_wait(&empty_b, (rep & 1) ^ 1);
+            asm volatile("st.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(scratch + lane * 16), "f"(1.f), "f"(2.f), "f"(3.f), "f"(4.f) : "memory");
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&full_b);
+        }
     }
     __syncthreads();
     fence_after_thread_sync();
@@ -100,10 +155,10 @@ __global__ void __launch_bounds__(128) tc_probe_kernel(const float* __restrict__
 // A [128,32], B [N,32] row-major; C[128,N] = reps * A * B^T (tf32-hi only); cycles[0] = clock64 ticks of the MMA batch
 extern "C" int dne_probe_mma(const float* d_A, const float* d_B, float* d_C, int N, int layout, int reps,
                              long long* d_cycles, void* stream) {
-    DNE_CHECK_ARG(d_A && d_B && d_C && d_cycles && (N == 32 || N == 64 || N == 128) && layout >= 0 && layout <= 2 && reps >= 1,
+    DNE_CHECK_ARG(d_A && d_B && d_C && d_cycles && (N == 32 || N == 64 || N == 128) && layout >= 0 && (layout & 15) <= 2 && reps >= 1,
                   "bad arguments");
     cudaStream_t st = (cudaStream_t)stream;
-    const int smem = 16384 + 128 * 32 * 4 + 1024;
+    const int smem = 16384 + 16384 + 16384 + 1024;
     if (N == 32) { cudaFuncSetAttribute(tc_probe_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
                    tc_probe_kernel<32><<<1, 128, smem, st>>>(d_A, d_B, d_C, layout, reps, d_cycles); }
     else if (N == 64) { cudaFuncSetAttribute(tc_probe_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);

@@ -8,19 +8,18 @@ L = F.lib()
 L.dne_probe_mma.argtypes = [C.c_void_p] * 3 + [C.c_int] * 3 + [C.c_void_p, C.c_void_p]
 L.dne_probe_mma.restype = C.c_int
 rs = np.random.RandomState(0)
-for N in (32, 64, 128):
+cyc = torch.zeros(1, dtype=torch.int64, device="cuda")
+names = {0: "chain (4 MMAs/iter)", 1: "6 MMAs + commit + wait / iter", 2: "chain + generic ST traffic (3 warps)",
+         3: "chain + st.shared traffic (3 warps)", 4: "ping-pong: stage warp -> full -> 6 MMAs -> commit(empty) / iter"}
+def run(N, mode, layout, reps):
     A = torch.from_numpy(rs.randn(128, 32).astype(np.float32)).cuda()
     B = torch.from_numpy(rs.randn(N, 32).astype(np.float32)).cuda()
     Cc = torch.zeros(128, N, device="cuda")
-    cyc = torch.zeros(1, dtype=torch.int64, device="cuda")
-    ref = (A.double() @ B.double().T).cpu().numpy()
+    F.check(L.dne_probe_mma(A.data_ptr(), B.data_ptr(), Cc.data_ptr(), N, (mode << 4) | layout, reps, cyc.data_ptr(), None))
+    torch.cuda.synchronize()
+    return int(cyc.item()) / reps
+for N in (32, 64, 128):
     for layout in (0, 1, 2):
-        F.check(L.dne_probe_mma(A.data_ptr(), B.data_ptr(), Cc.data_ptr(), N, layout, 1, cyc.data_ptr(), None))
-        torch.cuda.synchronize()
-        err = np.abs(Cc.cpu().numpy() - ref).max() / np.abs(ref).max()
-        res = []
-        for reps in (64, 512):
-            F.check(L.dne_probe_mma(A.data_ptr(), B.data_ptr(), Cc.data_ptr(), N, layout, reps, cyc.data_ptr(), None))
-            torch.cuda.synchronize()
-            res.append(int(cyc.item()) / (reps * 4))
-        print(f"N={N:3d} layout={layout} rel_err(1 rep, tf32-hi)={err:.2e}  cycles/MMA @64 reps={res[0]:.1f} @512 reps={res[1]:.1f}")
+        print(f"N={N} layout={layout} chain: {run(N, 0, layout, 512) / 4:.1f} cycles/MMA", flush=True)
+for mode in (1, 2, 3, 4):
+    print(f"N=64 mode {mode} [{names[mode]}]: {run(64, mode, 0, 512):.1f} cycles/iter", flush=True)
