@@ -75,9 +75,9 @@ conv_tc_kernel(SlotArgs sa, int64_t off_w, LayerEpi epi, const void* __restrict_
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     constexpr int NST = Cfg::NST;
     constexpr int STAGE_WARPS = TC_THREADS / 32;
+#ifdef DNE_CONV_TRACE        // dev timeline of one conv2 CTA (make EXTRA=-DDNE_CONV_TRACE; tools/conv_trace.py)
     const bool TRACE_ON = CIN == 32 && COUT == 64 && blockIdx.x == 0 && blockIdx.y == 7;
     TRACE(tid == 0, 0);
-#ifdef DNE_CONV_TRACE
     if (TRACE_ON && tid == 0) { unsigned long long ns; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(ns)); g_conv_trace[4] = (long long)ns; }
 #endif
 

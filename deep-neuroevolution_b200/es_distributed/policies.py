@@ -112,11 +112,10 @@ class Policy:
         self._theta = t
 
     def reinitialize(self):
-        """policies.py:42-44 + tf_util.py:122-130: column-normalise every weight matrix to its init std, zero
-        the biases (GA: applied to a raw noise slice, ga.py:256-260).  Runs on the device."""
-        import ctypes as C
-        from .es import default_noise
-        raise NotImplementedError("use dne_ga_materialize(mode=1) through es_distributed.ga")  # pragma: no cover
+        """policies.py:42-44 + tf_util.py:122-130: column-normalise every weight matrix of the CURRENT flat vector to
+        its init std and zero the biases (GA: applied to a raw noise slice, ga.py:256-260).  Init-time operation on the
+        device tensor (not on the rollout/update hot path; the GA driver uses dne_ga_materialize(mode=1) instead)."""
+        self._theta = reinitialize_flat(self.net, self._theta)
 
     # -- snapshot (policies.py:49-67) ------------------------------------------------------------------
     def _all_values(self):
@@ -316,3 +315,20 @@ class MujocoPolicy(Policy):
     def set_ob_stat(self, ob_mean, ob_std):
         self.ob_mean = torch.from_numpy(np.asarray(ob_mean, dtype=np.float32)).to(self.device)
         self.ob_std = torch.from_numpy(np.asarray(ob_std, dtype=np.float32)).to(self.device)
+
+
+def reinitialize_flat(net, theta: torch.Tensor) -> torch.Tensor:
+    """Column-normalise ``theta`` layer by layer (tf_util.py:122-130 ``normc_initializer`` applied to existing values):
+    each weight tensor viewed as [-1, n_out] gets every output column rescaled to L2 norm ``std``; biases -> 0;
+    a policy built from slim layers (ESAtariPolicy, policies.py:247-263) has no ``reinitialize`` ops in the reference
+    (``v.reinitialize`` raises AttributeError there), and the same error is raised here."""
+    if any(l.bn != F.BN_NONE for l in net.layers):
+        raise AttributeError("variables of {} carry no reinitialize op (only U.conv / U.dense variables do)".format(net.name))
+    out = theta.detach().clone().to(torch.float32).reshape(-1)
+    for l in net.layers:
+        n_w = (l.ksize * l.ksize * l.cin * l.cout) if l.kind == F.CONV else l.cin * l.cout
+        m = out[l.off_w:l.off_w + n_w].view(-1, l.cout)
+        m.mul_(float(l.std) / torch.sqrt((m * m).sum(dim=0, keepdim=True)))
+        if l.off_b >= 0:
+            out[l.off_b:l.off_b + l.cout] = 0
+    return out

@@ -197,3 +197,19 @@ def test_tabular_logger(tmp_path):
     tl.stop()
     txt = (tmp_path / "log.txt").read_text()
     assert "EpRewMean" in txt and "TimestepsSoFar" in txt
+
+
+def test_policy_reinitialize_matches_oracle():
+    """Policy.reinitialize (policies.py:42-44 + tf_util.py:122-158) == oracle.ga_reinitialize on the flat vector."""
+    import torch
+    from es_distributed import policies
+    from dne import nets
+    from oracle import oracle
+    for name in ("LargeModel", "Model", "MujocoPolicy"):
+        net, onet = nets.make_net(name), oracle.make_net(name)
+        th = np.random.RandomState(3).randn(net.num_params).astype(np.float32)
+        got = policies.reinitialize_flat(net, torch.from_numpy(th)).numpy()
+        want = oracle.ga_reinitialize(onet, th)
+        np.testing.assert_allclose(got, want, rtol=2e-6, atol=1e-7)
+    with pytest.raises(AttributeError):
+        policies.reinitialize_flat(nets.make_net("ESAtariPolicy"), torch.zeros(nets.make_net("ESAtariPolicy").num_params))
