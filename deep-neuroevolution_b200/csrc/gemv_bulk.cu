@@ -21,10 +21,12 @@ using namespace tc05;
 
 int g_dne_gemv_bulk = 1;
 int g_dne_gemv_ctas_per_sm = 2;
+int g_dne_gemv_stages = 6;           // shared-memory ring depth (2..GB_STAGES), dne_set_option("gemv_stages")
+int g_dne_gemv_prefetch = 0;         // L2 prefetch distance in stages (cp.async.bulk.prefetch.L2), dne_set_option("gemv_prefetch")
 
 constexpr int GB_CONSUMERS = 256;
 constexpr int GB_THREADS = GB_CONSUMERS + 32;      // + one producer warp
-constexpr int GB_STAGES = 6;
+constexpr int GB_STAGES = 8;                       // maximum ring depth (barrier arrays); the launch picks n_stages <= this
 constexpr int GB_STAGE_BYTES = 16384;
 constexpr int GB_RPR = 4;                          // rows per reader per stage: (16384/4N) / (256/(N/4)) = 4 for every N
 constexpr int GB_MAX_ROWS = 512;                   // rows per work item (x staging buffer)
@@ -32,11 +34,11 @@ constexpr int GB_MAX_ROWS = 512;                   // rows per work item (x stag
 template <int G>
 __global__ void __launch_bounds__(GB_THREADS)
 gemv_bulk_kernel(SlotArgs sa, GemvSrc src, const float* __restrict__ X, int64_t x_slot_stride, int K, int N,
-                 int rows_per_chunk, int n_chunks, int n_groups, float* __restrict__ part) {
+                 int rows_per_chunk, int n_chunks, int n_groups, float* __restrict__ part, int n_stages, int pf_dist) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
     float* stage_base = reinterpret_cast<float*>(smem);
-    float* red = reinterpret_cast<float*>(smem + GB_STAGES * GB_STAGE_BYTES);        // [RW][G][N+4]
+    float* red = reinterpret_cast<float*>(smem + n_stages * GB_STAGE_BYTES);        // [RW][G][N+4]
     __shared__ uint64_t full_bar[GB_STAGES], empty_bar[GB_STAGES];
     __shared__ float xs[G][GB_MAX_ROWS + 8];           // xs[g][1 + r] = x_g[k_beg + r];  xs[g][0] = x_g[k_beg - 1]
 
@@ -47,7 +49,7 @@ gemv_bulk_kernel(SlotArgs sa, GemvSrc src, const float* __restrict__ X, int64_t 
     const int n_items = n_groups * n_chunks;
 
     if (tid == 0) {
-        for (int s = 0; s < GB_STAGES; ++s) {
+        for (int s = 0; s < n_stages; ++s) {
             mbar_init(&full_bar[s], 1);
             mbar_init(&empty_bar[s], GB_CONSUMERS / 32);
         }
@@ -75,14 +77,34 @@ gemv_bulk_kernel(SlotArgs sa, GemvSrc src, const float* __restrict__ X, int64_t 
     if (warp == GB_CONSUMERS / 32) {
         // ===================== producer warp (one elected lane) =====================
         if (lane == 0) {
+            // L2 prefetch cursor: runs pf_dist stage-blocks ahead of the copy cursor (across work-item boundaries), so the
+            // HBM latency is covered by L2 and the shared-memory ring only has to cover the L2 -> SM latency.  That lets a
+            // shallow ring (1 CTA/SM, <= 64 KB) stream at HBM rate and leaves shared memory for a co-resident conv CTA.
+            int p_item = blockIdx.x - gridDim.x, p_r0 = 0, p_rows = 0;
+            const float* p_base = nullptr;
+            auto p_next_item = [&]() {
+                do { p_item += gridDim.x; } while (p_item < n_items && !item_active(p_item));
+                if (p_item < n_items) { int kb, a_; p_base = item_base(p_item, kb, p_rows, a_); p_r0 = 0; }
+            };
+            auto p_step = [&]() {                                // prefetch the cursor's block, then advance it
+                if (p_item >= n_items) return;
+                bulk_prefetch_l2(p_base + (int64_t)p_r0 * N, (uint32_t)min(RB, p_rows - p_r0) * N * 4);
+                p_r0 += RB;
+                if (p_r0 >= p_rows) p_next_item();
+            };
+            if (pf_dist > 0) {
+                p_next_item();
+                for (int d = 0; d < pf_dist; ++d) p_step();
+            }
             uint32_t it = 0;
             for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
                 if (!item_active(item)) continue;
                 int k_beg, rows, a;
                 const float* base = item_base(item, k_beg, rows, a);
                 for (int r0 = 0; r0 < rows; r0 += RB, ++it) {
-                    const int s = it % GB_STAGES;
-                    mbar_wait(&empty_bar[s], ((it / GB_STAGES) & 1) ^ 1);
+                    if (pf_dist > 0) p_step();
+                    const int s = it % n_stages;
+                    mbar_wait(&empty_bar[s], ((it / n_stages) & 1) ^ 1);
                     const uint32_t bytes = (uint32_t)min(RB, rows - r0) * N * 4;
                     mbar_arrive_expect_tx(&full_bar[s], bytes);
                     bulk_g2s(stage_base + (size_t)s * (GB_STAGE_BYTES / 4), base + (int64_t)r0 * N, bytes, &full_bar[s]);
@@ -119,7 +141,7 @@ gemv_bulk_kernel(SlotArgs sa, GemvSrc src, const float* __restrict__ X, int64_t 
         const bool do_wrap = (t == 0) && (a != 0);
 
         for (int r0 = 0; r0 < rows; r0 += RB, ++it) {
-            const int s = it % GB_STAGES;
+            const int s = it % n_stages;
             const int nr = min(RB, rows - r0);
             const int rl0 = rw * GB_RPR;                 // this reader's first row inside the stage (contiguous rows)
             // x multipliers: xm[g][j] = x[r0+rl0+j] (row itself), xm[g][-1 -> index 0] = x[r0+rl0-1] (wrap of the first row)
@@ -128,7 +150,7 @@ gemv_bulk_kernel(SlotArgs sa, GemvSrc src, const float* __restrict__ X, int64_t 
             for (int g = 0; g < G; ++g)
 #pragma unroll
                 for (int j = 0; j <= GB_RPR; ++j) xm[g][j] = xs[g][r0 + rl0 + j];        // xs index = 1 + (row - 1)
-            mbar_wait(&full_bar[s], (it / GB_STAGES) & 1);
+            mbar_wait(&full_bar[s], (it / n_stages) & 1);
             // explicit ld.shared (a C++ pointer into the re-aligned dynamic smem compiles to generic LD.E)
             const uint32_t rows_a = tc05::smem_u32(stage_base) + s * GB_STAGE_BYTES + (rl0 * NQ + t) * 16;
             if (nr == RB) {
@@ -227,7 +249,8 @@ int dne_launch_gemv_bulk(const SlotArgs& sa, const GemvSrc& src, int G, const fl
     const int RW = GB_CONSUMERS / (N / 4);
     if (GB_RPR * RW * N * 4 != GB_STAGE_BYTES || rows_per_chunk > GB_MAX_ROWS) return DNE_ERR_UNSUP;
     const int n_groups = (n_slots + G - 1) / G;
-    const size_t smem = (size_t)GB_STAGES * GB_STAGE_BYTES + (size_t)RW * G * (N + 4) * sizeof(float) + 128;
+    const int n_stages = g_dne_gemv_stages;
+    const size_t smem = (size_t)n_stages * GB_STAGE_BYTES + (size_t)RW * G * (N + 4) * sizeof(float) + 128;
     const int n_items = n_groups * n_chunks;
     int grid = g_dne_gemv_ctas_per_sm * sm_count;   // 1 CTA/SM leaves room for the other stream's conv CTAs to co-reside
     if (grid > n_items) grid = n_items;
@@ -235,21 +258,21 @@ int dne_launch_gemv_bulk(const SlotArgs& sa, const GemvSrc& src, int G, const fl
     if (G == 2) {
         if (!attr_done[2]) {
             cudaFuncSetAttribute(gemv_bulk_kernel<2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-            if (cudaFuncSetAttribute(gemv_bulk_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 108 * 1024) != cudaSuccess)
+            if (cudaFuncSetAttribute(gemv_bulk_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (GB_STAGES * 16 + 12) * 1024) != cudaSuccess)
                 return DNE_ERR_CUDA;
             attr_done[2] = true;
         }
         gemv_bulk_kernel<2><<<grid, GB_THREADS, smem, st>>>(sa, src, X, x_slot_stride, K, N, rows_per_chunk, n_chunks,
-                                                           n_groups, part);
+                                                           n_groups, part, n_stages, g_dne_gemv_prefetch);
     } else {
         if (!attr_done[1]) {
             cudaFuncSetAttribute(gemv_bulk_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-            if (cudaFuncSetAttribute(gemv_bulk_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 108 * 1024) != cudaSuccess)
+            if (cudaFuncSetAttribute(gemv_bulk_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (GB_STAGES * 16 + 12) * 1024) != cudaSuccess)
                 return DNE_ERR_CUDA;
             attr_done[1] = true;
         }
         gemv_bulk_kernel<1><<<grid, GB_THREADS, smem, st>>>(sa, src, X, x_slot_stride, K, N, rows_per_chunk, n_chunks,
-                                                           n_groups, part);
+                                                           n_groups, part, n_stages, g_dne_gemv_prefetch);
     }
     return 0;
 }

@@ -26,8 +26,11 @@ extern "C" int dne_debug_conv_trace(long long* host_out) {
 #else
 #define TRACE(cond, i) do { } while (0)
 #endif
-constexpr int TC_GROUPS = 4;                    // staging groups of 128 threads; group g owns smem stage g and stages chunks c = g (mod 4)
-constexpr int TC_THREADS = TC_GROUPS * 128;     // conv kernels: 16 staging warps ...
+#ifndef DNE_TC_GROUPS
+#define DNE_TC_GROUPS 3      // r01 A/B (tools/sweep_overlap.py): 3 groups (416 threads, 72 regs, no spills, 72 KB) >= 4 groups (56 regs, spills)
+#endif
+constexpr int TC_GROUPS = DNE_TC_GROUPS;        // staging groups of 128 threads; group g owns smem stage g and stages chunks c = g (mod TC_GROUPS)
+constexpr int TC_THREADS = TC_GROUPS * 128;     // conv kernels: the staging warps ...
 constexpr int TC_BLOCK = TC_THREADS + 32;       // ... + one MMA-issuing warp (warp-specialised, mbarrier pipeline, no block barriers)
 constexpr int TG_THREADS = 256;                 // theta GEMM / self-test
 
@@ -38,16 +41,20 @@ struct TcConvCfg {
     static constexpr int ROWS = MTC * 128;                       // A rows staged per CTA
     static constexpr int NCHUNK = K / KC;
     static constexpr int A_PLANE = ROWS * 16;                    // bytes per k-quad plane of A (= LBO of A)
-    static constexpr int B_PLANE = COUT * 16;                    // bytes per k-quad plane of B (= LBO of B)
+    // B tile = [B_hi ; B_lo] stacked along N (2*COUT rows per k-quad plane): ONE MMA with N = 2*COUT computes
+    // A_hi*B_hi (accumulator columns 0..COUT-1) and A_hi*B_lo (columns COUT..2*COUT-1) while reading A_hi once; the
+    // A_lo*B_hi term is a second MMA over the first COUT rows of the same tile.  2 MMAs / 14 KB of operand reads per
+    // k-step instead of 3 / 18 KB (the kernel is shared-memory-bandwidth bound); the two halves are summed in the epilogue.
+    static constexpr int B_PLANE = 2 * COUT * 16;                // bytes per k-quad plane of B (= LBO of B)
     static constexpr int A_BYTES = (KC / 4) * A_PLANE;           // one of {hi, lo}
-    static constexpr int B_BYTES = (KC / 4) * B_PLANE;
+    static constexpr int B_BYTES = (KC / 4) * B_PLANE;           // hi and lo together
     // uint8 frames are staged as their integer value 0..255 -- exact in TF32, so A needs no lo plane (and one MMA less per
     // k-step); the /255 of atari_wrappers.py:186 is applied to the accumulator in the epilogue
     static constexpr int A_PLANES = IN_U8 ? 1 : 2;
-    static constexpr int STAGE_BYTES = A_PLANES * A_BYTES + 2 * B_BYTES;
+    static constexpr int STAGE_BYTES = A_PLANES * A_BYTES + B_BYTES;
     static constexpr int NST = TC_GROUPS;                        // one shared-memory stage per staging group
     static constexpr int SMEM_BYTES = NST * STAGE_BYTES + 128;   // + alignment slack
-    static constexpr int ACC_COLS = MTC * COUT;
+    static constexpr int ACC_COLS = MTC * 2 * COUT;
     static constexpr int TMEM_COLS = (ACC_COLS <= 32) ? 32 : (ACC_COLS <= 64) ? 64 : (ACC_COLS <= 128) ? 128 : (ACC_COLS <= 256) ? 256 : 512;
     static constexpr int PASSES = ROWS / 32;                     // A rows per staging thread and chunk
     static constexpr int B_UNITS = COUT * (KC / 4);
@@ -105,7 +112,7 @@ conv_tc_kernel(SlotArgs sa, int64_t off_w, LayerEpi epi, const void* __restrict_
     __syncthreads();
     fence_after_thread_sync();
     const uint32_t tmem_base = tmem_base_s;
-    constexpr uint32_t IDESC = idesc_tf32(128, COUT);
+    constexpr uint32_t IDESC2 = idesc_tf32(128, 2 * COUT), IDESC1 = idesc_tf32(128, COUT);
 
     if (warp == STAGE_WARPS) {
         // ============ MMA warp: converged loop, descriptors in uniform registers, one elected lane issues ============
@@ -121,14 +128,13 @@ conv_tc_kernel(SlotArgs sa, int64_t off_w, LayerEpi epi, const void* __restrict_
             if (elect_one()) {
 #pragma unroll
                 for (int mt = 0; mt < MTC; ++mt) {
-                    const uint32_t d = tmem_base + mt * COUT;
+                    const uint32_t d = tmem_base + mt * 2 * COUT;
 #pragma unroll
                     for (int k8 = 0; k8 < KC / 8; ++k8) {
                         const uint64_t dAh = dA0 + so + (uint64_t)((2 * k8 * Cfg::A_PLANE + mt * 128 * 16) >> 4);
-                        const uint64_t dBh = dB0 + so + (uint64_t)((2 * k8 * Cfg::B_PLANE) >> 4);
-                        mma_tf32(d, dAh, dBh, IDESC, (c | k8) != 0);
-                        if (!IN_U8) mma_tf32(d, dAh + (uint64_t)(Cfg::A_BYTES >> 4), dBh, IDESC, 1);
-                        mma_tf32(d, dAh, dBh + (uint64_t)(Cfg::B_BYTES >> 4), IDESC, 1);
+                        const uint64_t dB = dB0 + so + (uint64_t)((2 * k8 * Cfg::B_PLANE) >> 4);
+                        mma_tf32(d, dAh, dB, IDESC2, (c | k8) != 0);                                  // A_hi * [B_hi ; B_lo]
+                        if (!IN_U8) mma_tf32(d, dAh + (uint64_t)(Cfg::A_BYTES >> 4), dB, IDESC1, 1);  // A_lo * B_hi
                     }
                 }
                 mma_commit(&empty_bar[st]);                      // stage reusable once these MMAs have read it
@@ -167,16 +173,14 @@ conv_tc_kernel(SlotArgs sa, int64_t off_w, LayerEpi epi, const void* __restrict_
         }
         // B: unit u = tg + i*128 -> (column n = u % COUT, k-quad u / COUT); element offset of its first k row
         constexpr int BPT = Cfg::B_PER_THREAD;
-        int b_off[BPT];
-#pragma unroll
-        for (int i = 0; i < BPT; ++i) {
-            const int u = tg + i * 128;
-            b_off[i] = 4 * (u / COUT) * COUT + (u % COUT);
-        }
+        // (128 % COUT == 0: unit i of a thread is the same column n, k-quad q0 + i*(128/COUT))
+        static_assert(128 % COUT == 0, "B unit map");
+        const int b_off0 = 4 * (tg / COUT) * COUT + (tg % COUT);             // global element offset of unit 0's first k row
+        const int b_st0 = (tg / COUT) * Cfg::B_PLANE + (tg % COUT) * 16;     // byte offset of unit 0's hi quad in the B tile
+        constexpr int B_OFF_STEP = 4 * 128, B_ST_STEP = (128 / COUT) * Cfg::B_PLANE;
         const uint32_t sA_hi = smem_u32(smem) + g * Cfg::STAGE_BYTES + q * Cfg::A_PLANE + (wg * 8 + (lane & 7)) * 16;   // + i*512 per pass
         const uint32_t sA_lo = sA_hi + Cfg::A_BYTES;
-        const uint32_t sB_hi = smem_u32(smem) + g * Cfg::STAGE_BYTES + Cfg::A_PLANES * Cfg::A_BYTES + tg * 16;         // + i*2048 per unit
-        const uint32_t sB_lo = sB_hi + Cfg::B_BYTES;
+        const uint32_t sB = smem_u32(smem) + g * Cfg::STAGE_BYTES + Cfg::A_PLANES * Cfg::A_BYTES;
 
         for (int c = g, it = 0; c < Cfg::NCHUNK; c += TC_GROUPS, ++it) {
             // ---- raw global loads of the chunk (issued before the stage wait so that their latency overlaps it) ----
@@ -201,8 +205,8 @@ conv_tc_kernel(SlotArgs sa, int64_t off_w, LayerEpi epi, const void* __restrict_
                 if (tg + i * 128 < Cfg::B_UNITS) {
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
-                        rawB_t[i][j] = tw[fb + b_off[i] + j * COUT];
-                        rawB_n[i][j] = nz[fb + b_off[i] + j * COUT];
+                        rawB_t[i][j] = tw[fb + b_off0 + i * B_OFF_STEP + j * COUT];
+                        rawB_n[i][j] = nz[fb + b_off0 + i * B_OFF_STEP + j * COUT];
                     }
                 }
             }
@@ -237,8 +241,8 @@ conv_tc_kernel(SlotArgs sa, int64_t off_w, LayerEpi epi, const void* __restrict_
                     split_tf32_rn(perturbed(rawB_t[i][1], s, rawB_n[i][1]), hi.y, lo.y);
                     split_tf32_rn(perturbed(rawB_t[i][2], s, rawB_n[i][2]), hi.z, lo.z);
                     split_tf32_rn(perturbed(rawB_t[i][3], s, rawB_n[i][3]), hi.w, lo.w);
-                    sts128(sB_hi + i * 2048, hi);                    // unit u at u*16 == (u / COUT) * B_PLANE + (u % COUT) * 16
-                    sts128(sB_lo + i * 2048, lo);
+                    sts128(sB + b_st0 + i * B_ST_STEP, hi);
+                    sts128(sB + b_st0 + i * B_ST_STEP + COUT * 16, lo);
                 }
             }
             fence_proxy_async_smem();                            // generic-proxy writes -> async proxy
@@ -259,8 +263,11 @@ conv_tc_kernel(SlotArgs sa, int64_t off_w, LayerEpi epi, const void* __restrict_
         for (int p = 0; p < MTC * NJ; ++p) {
             if (p % TC_GROUPS != g) continue;
             const int mt = p / NJ, n0 = (p % NJ) * 16;
-            float v[16];
-            tmem_ld16(tmem_base + ((uint32_t)(wg * 32) << 16) + (uint32_t)(mt * COUT + n0), v);
+            float v[16], v2[16];
+            tmem_ld16(tmem_base + ((uint32_t)(wg * 32) << 16) + (uint32_t)(mt * 2 * COUT + n0), v);
+            tmem_ld16(tmem_base + ((uint32_t)(wg * 32) << 16) + (uint32_t)(mt * 2 * COUT + COUT + n0), v2);
+#pragma unroll
+            for (int x = 0; x < 16; ++x) v[x] += v2[x];
             const int m = row0 + mt * 128 + wg * 32 + lane;
             if (m < Cfg::M) {
                 float4* dst = reinterpret_cast<float4*>(out + (int64_t)m * COUT + n0);

@@ -12,7 +12,7 @@ from typing import Optional
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdne.so")
+LIB_PATH = os.environ.get("DNE_LIB") or os.path.join(_HERE, "libdne.so")     # DNE_LIB: dev override (A/B builds)
 
 DNE_MAX_LAYERS = 8
 CONV, DENSE = 0, 1
