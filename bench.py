@@ -2,7 +2,7 @@
 """bench.py -- env-steps/sec across the ES population (BASELINE.json metric) on N B200s of one node.
 
 Workload (BASELINE.json configs[1]): Frostbite-shaped ES generation, population 1000
-(n = 500 antithetic pairs), LargeModel conv policy (P = 4,052,658, 18 actions), 256 env slots per GPU, synthetic
+(n = 500 antithetic pairs), LargeModel conv policy (P = 4,052,658, 18 actions), a resident env-slot pair per local antithetic pair (<= 1024 slots per GPU), synthetic
 uint8 84x84x4 observations, fixed episode length T (default 1000 env steps), population sharded over the ranks.
 One "step" = one GENERATION: rollouts of this rank's shard of the population for T ticks each, then the update
 (all_gather returns -> centred ranks -> ES gradient over the local noise indices -> all_reduce(g) -> Adam).
@@ -35,7 +35,7 @@ import numpy as np   # noqa: E402
 
 NET = "LargeModel"
 POP = 1000
-SLOTS = 512
+SLOTS = 1024           # upper bound of resident environment slots per GPU; the run uses min(SLOTS, 2 * local pairs)
 SIGMA, L2, LR = 0.005, 0.005, 0.01          # configurations/frostbite_es.json
 
 
@@ -143,11 +143,16 @@ def run_b200(args):
     # ------------------------------------------------------------------ value: device-resident generation
     lo, hi = shard.shard_bounds(n_pairs, rank, world)
     upd = ESUpdate(ctx, theta0, "adam", stepsize=LR)
-    # Two slot tables of slots/2 on two streams by default: one table's conv chain (shared-memory / tensor bound)
-    # overlaps the other's HBM-bound noise GEMV (tools/sweep_overlap.py, r01: 512 slots: 1 table 594K, 2 tables 640K
-    # env-steps/s).  DNE_BENCH_STREAMS=1 gives the serial schedule; DNE_BENCH_PHASED=1 adds the phase-event hand-off.
-    NS = int(os.environ.get("DNE_BENCH_STREAMS", "2"))
-    part = (args.slots // NS) // 2 * 2                          # whole antithetic pairs per table
+    # Slot tables: every local antithetic pair gets a resident slot pair when it fits (pop 1000 on one GPU: 1000 slots,
+    # one wave per generation -- no under-filled second wave), split over NS tables on NS streams so that one table's
+    # conv chain (shared-memory / tensor bound) overlaps another's HBM-bound noise GEMV (tools/sweep_overlap.py, r01:
+    # 256 slots x 1 table 560K, 512 x 2 tables 630-650K, 1024 x 4 tables 655-660K env-steps/s).
+    # DNE_BENCH_STREAMS overrides NS; DNE_BENCH_PHASED=1 adds the phase-event hand-off (dne_set_phase_events).
+    pairs_local = hi - lo
+    slots = max(2, min(args.slots, 2 * pairs_local))
+    NS = int(os.environ.get("DNE_BENCH_STREAMS", "4" if slots >= 768 else ("2" if slots >= 192 else "1")))
+    part = 2 * (-(-(slots // 2) // NS))                          # whole antithetic pairs per table
+    slots = part * NS
     sfs = [SlotForward(ctx, net, part) for _ in range(NS)]
     streams = [torch.cuda.Stream(device=dev) for _ in range(NS)]
     PHASED = os.environ.get("DNE_BENCH_PHASED", "1" if NS > 2 else "0") == "1"
@@ -156,9 +161,9 @@ def run_b200(args):
     for e in phase_ev:
         e.record()                                               # materialise the handles
     R = 4                                                        # observation pool blocks, rotated every tick
-    pool = torch.randint(0, 256, (R, args.slots, 84, 84, 4), dtype=torch.uint8, device=dev)
-    rew_pool = (torch.rand(64, args.slots, device=dev) < 0.05).float() * 10.0
-    ret_acc = torch.zeros(args.slots, device=dev)
+    pool = torch.randint(0, 256, (R, slots, 84, 84, 4), dtype=torch.uint8, device=dev)
+    rew_pool = (torch.rand(64, slots, device=dev) < 0.05).float() * 10.0
+    ret_acc = torch.zeros(slots, device=dev)
     idx_stream = np.random.RandomState(1)
     tally = {"launches": 0, "pairs": 0}
     net_ref = C.byref(net.desc)
@@ -175,7 +180,7 @@ def run_b200(args):
         idx_all = np.array([noise.sample_index(idx_stream, P) for _ in range(n_pairs)], dtype=np.int64)
         my = idx_all[lo:hi]
         returns = torch.zeros(len(my), 2, device=dev)
-        pairs_per_wave = args.slots // 2
+        pairs_per_wave = slots // 2
         cur = torch.cuda.current_stream()
         for w0 in range(0, len(my), pairs_per_wave):
             wave = my[w0:w0 + pairs_per_wave]
@@ -302,7 +307,8 @@ def run_b200(args):
         tabular_logger.set_quiet(True)          # stdout carries exactly one JSON line
         ES.set_default_noise(noise)
         ES._STATE["ctx"] = ctx
-        env = SyntheticAtariEnv(args.slots, episode_len=T, seed=rank)
+        slots_e2e = -(-slots // 4) * 4                       # RolloutRunner: multiple of group (2) x pipeline halves (2)
+        env = SyntheticAtariEnv(slots_e2e, episode_len=T, seed=rank)
         marks = {}
 
         io = {"h2d": 0, "d2h": 0}
@@ -316,7 +322,7 @@ def run_b200(args):
                 shard.barrier()
                 torch.cuda.synchronize()
                 marks[it] = time.perf_counter()
-        ES.run_master(None, None, exp_dict(args), max_iterations=args.warmup + args.steps, n_slots=args.slots,
+        ES.run_master(None, None, exp_dict(args), max_iterations=args.warmup + args.steps, n_slots=slots_e2e,
                       env=env, noise=noise, seed=0, on_iteration=on_it)
         dt = marks[args.warmup + args.steps] - marks[args.warmup]
         tt = torch.tensor([dt], dtype=torch.float64, device=dev)
@@ -338,9 +344,9 @@ def run_b200(args):
             "metric": "env-steps/sec across ES population (whole box)", "value": value, "unit": "env-steps/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_val / args.steps,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"frostbite_es_pop{args.pop}_LargeModel_{args.slots}slots_T{T}",
+            "config": {"workload": f"frostbite_es_pop{args.pop}_LargeModel_T{T}",
                        "population": args.pop, "noise_pairs": n_pairs, "policy": "LargeModel (P=4052658, 18 actions)",
-                       "env_slots_per_gpu": args.slots, "episode_len": T, "noise_table": args.noise_count,
+                       "env_slots_per_gpu": slots, "slot_tables": NS, "episode_len": T, "noise_table": args.noise_count,
                        "sharding": f"population over {world} rank(s); all_gather(returns)+all_reduce(g)",
                        "l2": "inputs larger than L2 (>=1 GB of noise slices streamed per tick)",
                        "step": "one generation (rollouts + update)"},
@@ -438,7 +444,7 @@ def run_reference(args):
         "unit": "env-steps/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": float(np.mean(times)) * 1e3, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"frostbite_es_pop{args.pop}_LargeModel_{args.slots}slots_T{args.episode_len}",
+        "config": {"workload": f"frostbite_es_pop{args.pop}_LargeModel_T{args.episode_len}",
                    "population": args.pop, "policy": "LargeModel (P=4052658, 18 actions)", "episode_len": args.episode_len},
         "cpu_baseline": {"value": v, "unit": "env-steps/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},

@@ -64,6 +64,7 @@ _SIGS = {
     "dne_set_option": [C.c_char_p, C.c_int],
     "dne_set_phase_events": [_P, _P, _P, C.c_int],
     "dne_test_tc_gemm": [_P, _P, _P, C.c_int, C.c_int, _P],
+    "dne_probe_mma": [_P, _P, _P, C.c_int, C.c_int, C.c_int, _P, _P],
     "dne_profile_enable": [_P, C.c_int, C.c_int],
     "dne_profile_read": [_P, C.POINTER(C.c_int), C.POINTER(C.c_double)],
     "dne_ga_mutate": [_P, _P, C.c_int64, C.c_float, C.c_int64, _P, _P],

@@ -91,11 +91,21 @@ int         dne_abi_sizes(int* layer_desc_bytes, int* net_desc_bytes);
  * dne_profile_enable/read: CUDA-event timing of every launch of the dominant HBM-bound kernel
  * (dense_noise_gemv) on the stream it is launched on; read() synchronises the device. */
 long long   dne_launch_count(int reset);
-/* Runtime switches: "conv_tc" = 1 (default) runs the member convolutions on the tensor cores (tcgen05.mma kind::tf32,
- * 3xTF32 split, TMEM accumulators); 0 selects the fp32 SIMT convolution kernels (kept for A/B parity checks). */
+/* Runtime switches (process-wide):
+ *   "conv_tc" = 1 (default): member convolutions + the shared-theta GEMM on the tensor cores (tcgen05.mma kind::tf32,
+ *               3xTF32 split, TMEM accumulators); 0 selects the fp32 SIMT kernels (kept for A/B parity checks).
+ *   "gemv_bulk" = 1 (default): noise GEMV through the cp.async.bulk shared-memory ring; 0 = plain-LDG kernel.
+ *   "gemv_ctas_per_sm" = 1|2 (default 2), "gemv_stages" = 2..8 (default 6): persistent-grid size / ring depth of it.
+ *   "gemv_prefetch" = 0..256 (default 0): L2 prefetch distance in 16 KB stages (measured slower on B200; off). */
 int         dne_set_option(const char* name, int value);
 /* Self-test of the tcgen05 plumbing: C[128,N] = A[128,K] * B[N,K]^T (row-major, K % 32 == 0, N in {16,32,64}). */
 int         dne_test_tc_gemm(const float* d_A, const float* d_B, float* d_C, int K, int N, void* stream);
+/* Micro-probe of tcgen05.mma kind::tf32 (tools/probe_mma.py): one CTA, A [128,32] / B [N,32] row-major staged once,
+ * `reps` batches of MMAs accumulated; d_cycles[0] = clock64 ticks of the batch.  layout = smem operand layout
+ * (0 no-swizzle, 1 SWIZZLE_32B, 2 SWIZZLE_128B) | mode << 4 (0 chain, 1 commit+wait per 6 MMAs, 2/3 chain under
+ * generic / st.shared store traffic, 4 full/empty ping-pong with a staging warp). */
+int         dne_probe_mma(const float* d_A, const float* d_B, float* d_C, int N, int layout, int reps,
+                          long long* d_cycles, void* stream);
 int         dne_profile_enable(dne_ctx* ctx, int on, int capacity);
 int         dne_profile_read(dne_ctx* ctx, int* n_launches, double* total_ms);
 

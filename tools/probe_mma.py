@@ -5,8 +5,6 @@ sys.path[:0] = [ROOT, os.path.join(ROOT, "deep-neuroevolution_b200")]
 import numpy as np, torch
 from dne import _ffi as F
 L = F.lib()
-L.dne_probe_mma.argtypes = [C.c_void_p] * 3 + [C.c_int] * 3 + [C.c_void_p, C.c_void_p]
-L.dne_probe_mma.restype = C.c_int
 rs = np.random.RandomState(0)
 cyc = torch.zeros(1, dtype=torch.int64, device="cuda")
 names = {0: "chain (4 MMAs/iter)", 1: "6 MMAs + commit + wait / iter", 2: "chain + generic ST traffic (3 warps)",
