@@ -354,7 +354,7 @@ def run_b200(args):
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
             "noise_table_build_s": t_noise,
         }
-        print(json.dumps(line))
+        _emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -439,7 +439,7 @@ def run_reference(args):
     v = float(np.mean(vals))
     sample = (f"per step: {cores} antithetic pairs x {Ts} env steps on {cores} forked 1-thread workers + master update "
               f"on {n_upd} slices scaled to {args.pop // 2}; generation time extrapolated to pop {args.pop} x T {args.episode_len}")
-    print(json.dumps({
+    _emit({
         "impl": "reference", "metric": "env-steps/sec across ES population (whole box)", "value": v,
         "unit": "env-steps/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": float(np.mean(times)) * 1e3, "higher_is_better": True, "scaling": "strong",
@@ -449,13 +449,23 @@ def run_reference(args):
         "cpu_baseline": {"value": v, "unit": "env-steps/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "reference TF/redis workers cannot run (tensorflow, gym, ALE, redis absent): CPU restatement of "
-                "es.py:411-426 + policies.py:399-409 and es.py:273-301 (oracle/cpu_worker.py)"}))
+                "es.py:411-426 + policies.py:399-409 and es.py:273-301 (oracle/cpu_worker.py)"})
+
+
+def _emit(obj):
+    """The ONE JSON line of the contract, written to the process's original stdout."""
+    os.write(_REAL_STDOUT, (json.dumps(obj) + "\n").encode())
 
 
 if __name__ == "__main__":
+    # stdout carries exactly one JSON line: everything else that libraries print to fd 1 (NCCL's version banner,
+    # loggers) is routed to stderr for the whole run.
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     a = parse()
     if a.impl == "cpu-sample":
-        print(json.dumps(cpu_sample(a)))
+        _emit(cpu_sample(a))
     elif a.impl == "reference":
         run_reference(a)
     else:
