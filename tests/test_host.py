@@ -112,7 +112,7 @@ sys.path[:0] = [%(root)r, os.path.join(%(root)r, "deep-neuroevolution_b200")]
 from dne import shard
 from oracle import oracle as O
 rank, world, _ = shard.init_from_env("gloo")
-assert world == 2
+assert world == %(world)d
 # one "generation": every rank draws the same index stream, evaluates its shard (fake returns = f(index)),
 # gathers, ranks, forms its partial gradient with the GLOBAL denominator, all-reduces.
 seed = shard.broadcast_seed(None if rank == 0 else 12345)
@@ -140,12 +140,14 @@ dist.destroy_process_group()
 '''
 
 
-def test_sharded_generation_bookkeeping_gloo_world2(tmp_path):
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_generation_bookkeeping_gloo_world2(tmp_path, world):
+    """world 2 and 3: 21 units -> ragged shards (10/11, 7/7/7), padded all_gather, partial gradients all-reduced."""
     script = tmp_path / "w.py"
-    script.write_text(_GLOO_WORKER % {"root": ROOT})
+    script.write_text(_GLOO_WORKER % {"root": ROOT, "world": world})
     env = dict(os.environ, MASTER_ADDR="127.0.0.1")
-    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
-                        "--master-addr", "127.0.0.1", "--master-port", "29571", str(script)],
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+                        "--master-addr", "127.0.0.1", "--master-port", str(29569 + world), str(script)],
                        capture_output=True, text=True, timeout=240, env=env)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "GLOO_OK" in r.stdout
