@@ -150,7 +150,7 @@ def run_b200(args):
     # DNE_BENCH_STREAMS overrides NS; DNE_BENCH_PHASED=1 adds the phase-event hand-off (dne_set_phase_events).
     pairs_local = hi - lo
     slots = max(2, min(args.slots, 2 * pairs_local))
-    NS = int(os.environ.get("DNE_BENCH_STREAMS", "4" if slots >= 768 else ("2" if slots >= 192 else "1")))
+    NS = int(os.environ.get("DNE_BENCH_STREAMS", "4" if slots >= 384 else ("2" if slots >= 192 else "1")))
     part = 2 * (-(-(slots // 2) // NS))                          # whole antithetic pairs per table
     slots = part * NS
     sfs = [SlotForward(ctx, net, part) for _ in range(NS)]
