@@ -2,7 +2,7 @@
 """bench.py -- env-steps/sec across the ES population (BASELINE.json metric) on N B200s of one node.
 
 Workload (BASELINE.json configs[1]): Frostbite-shaped ES generation, population 1000
-(n = 500 antithetic pairs), LargeModel conv policy (P = 4,052,658, 18 actions), a resident env-slot pair per local antithetic pair (<= 1024 slots per GPU), synthetic
+(n = 500 antithetic pairs), LargeModel conv policy (P = 4,052,658, 18 actions), 256 resident env slots per GPU (--slots), synthetic
 uint8 84x84x4 observations, fixed episode length T (default 1000 env steps), population sharded over the ranks.
 One "step" = one GENERATION: rollouts of this rank's shard of the population for T ticks each, then the update
 (all_gather returns -> centred ranks -> ES gradient over the local noise indices -> all_reduce(g) -> Adam).
@@ -35,7 +35,7 @@ import numpy as np   # noqa: E402
 
 NET = "LargeModel"
 POP = 1000
-SLOTS = 1024           # upper bound of resident environment slots per GPU; the run uses min(SLOTS, 2 * local pairs)
+SLOTS = 256            # BASELINE.json configs[1]: 256 parallel envs per GPU (the run uses min(SLOTS, 2 * local pairs))
 SIGMA, L2, LR = 0.005, 0.005, 0.01          # configurations/frostbite_es.json
 
 
@@ -143,14 +143,15 @@ def run_b200(args):
     # ------------------------------------------------------------------ value: device-resident generation
     lo, hi = shard.shard_bounds(n_pairs, rank, world)
     upd = ESUpdate(ctx, theta0, "adam", stepsize=LR)
-    # Slot tables: every local antithetic pair gets a resident slot pair when it fits (pop 1000 on one GPU: 1000 slots,
-    # one wave per generation -- no under-filled second wave), split over NS tables on NS streams so that one table's
-    # conv chain (shared-memory / tensor bound) overlaps another's HBM-bound noise GEMV (tools/sweep_overlap.py, r01:
-    # 256 slots x 1 table 560K, 512 x 2 tables 630-650K, 1024 x 4 tables 655-660K env-steps/s).
+    # Slot tables.  Default = BASELINE configs[1]: 256 resident env slots per GPU in ONE table on one stream (four waves
+    # of 128 pairs per generation at pop 1000): every kernel runs alone, so the per-launch GEMV timing in `roofline` and
+    # the ncu launch list describe the same schedule.  `--slots 1024` gives every antithetic pair a resident slot pair
+    # (one wave per generation) split over 4 tables on 4 streams, whose conv chains overlap each other's HBM-bound
+    # GEMV: r01 624K vs 527-540K env-steps/s (profiles/r01_bench_n1_1000slots.json; tools/sweep_overlap.py).
     # DNE_BENCH_STREAMS overrides NS; DNE_BENCH_PHASED=1 adds the phase-event hand-off (dne_set_phase_events).
     pairs_local = hi - lo
     slots = max(2, min(args.slots, 2 * pairs_local))
-    NS = int(os.environ.get("DNE_BENCH_STREAMS", "4" if slots >= 384 else ("2" if slots >= 192 else "1")))
+    NS = int(os.environ.get("DNE_BENCH_STREAMS", "4" if slots >= 768 else ("2" if slots >= 384 else "1")))
     part = 2 * (-(-(slots // 2) // NS))                          # whole antithetic pairs per table
     slots = part * NS
     sfs = [SlotForward(ctx, net, part) for _ in range(NS)]
