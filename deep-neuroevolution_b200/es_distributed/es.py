@@ -132,7 +132,7 @@ def get_ref_batch(env: BatchEnv, batch_size=32, rs=None):
         _, done = env.step(slot, env.random_actions(1, rs))
         if hasattr(env, "advance"):
             env.advance()
-        ref_batch.append(np.array(env.obs_block(0, 1)[0]))
+        ref_batch.append(env.obs_block(0, 1)[0].numpy().copy())
         if done[0]:
             env.reset(slot)
     return ref_batch

@@ -1,6 +1,6 @@
 """``python -m es_distributed.main`` -- the reference CLI (es_distributed/main.py:29-86) on the B200 engine.
 
-  master   --algo {es,ns-es,nsr-es,ga}  --exp_file / --exp_str  [--master_socket_path] [--log_dir]
+  master   --algo {es,ns-es,nsr-es,ga,rs}  --exp_file / --exp_str  [--master_socket_path] [--log_dir]
   workers  --algo ... --master_host --master_port --relay_socket_path --num_workers
 
 There is no redis: the "workers" of the reference are the GPU ranks of one torchrun job and every rank runs
@@ -36,6 +36,8 @@ def import_algo(name):
         from . import nses as algo
     elif name == 'ga':
         from . import ga as algo
+    elif name == 'rs':
+        from . import rs as algo
     else:
         raise NotImplementedError(name)
     return algo

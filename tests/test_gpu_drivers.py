@@ -126,6 +126,31 @@ def test_ga_run_master_bookkeeping(noise, host_noise, tmp_path):
         prev_pop, prev_score = ex["population"], ex["population_score"]
 
 
+def test_rs_run_master_keeps_best_candidate(noise, host_noise, tmp_path):
+    """rs.py:112-116: the policy becomes reinitialize(noise[idx]) of the best-scoring candidate seen so far."""
+    from es_distributed import rs as RS
+    env = SyntheticAtariEnv(8, episode_len=4, seed=6, num_actions=6)
+    log = []
+    RS.set_default_noise(noise)
+    best_seed, best_score = RS.run_master(None, str(tmp_path), json.loads(json.dumps(FROSTBITE_GA)), max_iterations=3,
+                                          n_slots=8, env=env, noise=noise, seed=3,
+                                          on_iteration=lambda it, st, ex: log.append((it, st, dict(ex, theta=ex["theta"].clone()))))
+    assert len(log) == 3
+    net = O.make_net("GAAtariPolicy", num_actions=6)
+    run_best, run_seed = -np.inf, None
+    for it, st, ex in log:
+        r, idx = ex["returns_n2"], ex["noise_inds_n"]
+        assert r.shape == ex["lengths_n2"].shape == (len(idx), 1) and len(idx) == 12 and r.dtype == np.float32
+        assert np.all(ex["lengths_n2"] == 4) and st["EpisodesThisIter"] == 12
+        j = int(np.argmax(r))
+        if r[j, 0] > run_best:
+            run_best, run_seed = float(r[j, 0]), int(idx[j])
+        assert ex["best_score"] == run_best and ex["best_seed"] == run_seed
+        want = O.ga_reinitialize(net, host_noise[run_seed:run_seed + net.num_params])
+        np.testing.assert_allclose(ex["theta"].cpu().numpy(), want, rtol=1e-6, atol=1e-9)
+    assert (best_seed, best_score) == (run_seed, run_best)
+
+
 def test_nsr_run_master_novelty_and_update(noise, host_noise, tmp_path):
     from es_distributed import nses as NS
     env = SyntheticAtariEnv(8, episode_len=(3, 7), seed=9)
