@@ -117,40 +117,78 @@ class Policy:
         device tensor (not on the rollout/update hot path; the GA driver uses dne_ga_materialize(mode=1) instead)."""
         self._theta = reinitialize_flat(self.net, self._theta)
 
-    # -- snapshot (policies.py:49-67) ------------------------------------------------------------------
+    # -- snapshot (policies.py:49-67, 219-249) --------------------------------------------------------------
+    # On-disk format = the reference's: one dataset per variable under its TF name + attrs 'name' and
+    # 'args_and_kwargs' (pickle).  Container: HDF5 when h5py is importable (reference snapshots load unchanged),
+    # else an .npz with the same keys next to the requested name (h5py is not in this image; SURVEY.md 8f rank 2).
     def _all_values(self):
         theta = self.get_trainable_flat()
-        return {name: theta[off:off + int(np.prod(shp))].reshape(shp) for name, shp, off in self.trainable_variables}
+        vals = {name: theta[off:off + int(np.prod(shp))].reshape(shp) for name, shp, off in self.trainable_variables}
+        if self.ob_mean is not None and self.ob_std is not None:        # MujocoPolicy keeps them as variables
+            scope = type(self).__name__
+            vals["{}/ob_mean:0".format(scope)] = self.ob_mean.cpu().numpy()
+            vals["{}/ob_std:0".format(scope)] = self.ob_std.cpu().numpy()
+        return vals
 
     def save(self, filename):
         assert filename.endswith('.h5')
-        try:
-            import h5py
-        except ImportError:
-            h5py = None
-        vals = self._all_values()
-        blob = pickle.dumps((self.args, {k: v for k, v in self.kwargs.items()}), protocol=-1)
-        if h5py is not None:
-            with h5py.File(filename, 'w', libver='latest') as f:
-                for k, v in vals.items():
-                    f[k] = v
-                f.attrs['name'] = type(self).__name__
-                f.attrs['args_and_kwargs'] = np.void(blob)
-        else:   # h5py is not in this image: same keys, numpy container (SURVEY.md 8f rank 2)
-            np.savez(filename + ".npz", __name__=type(self).__name__, __args__=np.frombuffer(blob, dtype=np.uint8), **vals)
+        _write_snapshot(filename, type(self).__name__, pickle.dumps((self.args, dict(self.kwargs)), protocol=-1),
+                        self._all_values())
 
     @classmethod
     def Load(cls, filename, extra_kwargs=None):
-        data = np.load(filename if filename.endswith(".npz") else filename + ".npz", allow_pickle=False)
-        args, kwargs = pickle.loads(data["__args__"].tobytes())
+        _, blob, data = _read_snapshot(filename)
+        args, kwargs = pickle.loads(blob)
         if extra_kwargs:
             kwargs.update(extra_kwargs)
         policy = cls(*args, **kwargs)
-        theta = policy.get_trainable_flat()
-        for name, shp, off in policy.trainable_variables:
-            theta[off:off + int(np.prod(shp))] = data[name].reshape(-1)
-        policy.set_trainable_flat(theta)
+        policy.set_all_vars(*[data[name] for name, _, _ in policy.all_variables])
+        policy._load_ob_stat(data)
         return policy
+
+    def set_all_vars(self, *vals):
+        """policies.py:36-40: assign every variable, in ``all_variables`` order."""
+        assert len(vals) == len(self.all_variables), "expected {} arrays".format(len(self.all_variables))
+        theta = self.get_trainable_flat()
+        for (name, shp, off), v in zip(self.all_variables, vals):
+            v = np.asarray(v, dtype=np.float32)
+            assert int(v.size) == int(np.prod(shp)), "{}: shape {} != {}".format(name, v.shape, shp)
+            theta[off:off + v.size] = v.reshape(-1)
+        self.set_trainable_flat(theta)
+
+    def _load_ob_stat(self, data):
+        scope = type(self).__name__
+        km, ks = "{}/ob_mean:0".format(scope), "{}/ob_std:0".format(scope)
+        if km in data and ks in data and np.all(np.isfinite(data[km])) and np.all(np.isfinite(data[ks])):
+            self.set_ob_stat(np.asarray(data[km]), np.asarray(data[ks]))
+
+    def initialize_from(self, filename, ob_stat=None):
+        """policies.py:219-249: initialise from a snapshot of the SAME architecture (variable names) whose arrays may be
+        smaller than this policy's: the loaded values fill the leading sub-array of each variable."""
+        _, _, data = _read_snapshot(filename)
+        own = {name for name, _, _ in self.all_variables}
+        scope = type(self).__name__
+        f_names = {k for k in data if not k.endswith(("ob_mean:0", "ob_std:0"))}
+        assert own == f_names, 'Variable names do not match'
+        theta = self.get_trainable_flat()
+        for name, shp, off in self.all_variables:
+            f_val = np.asarray(data[name], dtype=np.float32)
+            f_shp = f_val.shape
+            assert len(shp) == len(f_shp) and all(a >= b for a, b in zip(shp, f_shp)), \
+                'This policy must have more weights than the policy to load'
+            cur = theta[off:off + int(np.prod(shp))].reshape(shp)
+            cur[tuple(np.s_[:n] for n in f_shp)] = f_val
+        self.set_trainable_flat(theta)
+        km, ks = "{}/ob_mean:0".format(scope), "{}/ob_std:0".format(scope)
+        if km in data and ks in data:
+            dim = int(self.net.ob_dim)
+            init_mean = np.zeros(dim, np.float32)                   # policies.py:236-241: defaults 0 / 0.001
+            init_std = np.full(dim, 0.001, np.float32)
+            init_mean[:len(data[km])] = data[km]
+            init_std[:len(data[ks])] = data[ks]
+            if ob_stat is not None:
+                ob_stat.set_from_init(init_mean, init_std, init_count=1e5)
+            self.set_ob_stat(init_mean, init_std)
 
     # -- acting ------------------------------------------------------------------------------------------
     def _engine(self, n):
@@ -332,3 +370,34 @@ def reinitialize_flat(net, theta: torch.Tensor) -> torch.Tensor:
         if l.off_b >= 0:
             out[l.off_b:l.off_b + l.cout] = 0
     return out
+
+
+def _write_snapshot(filename, name, blob: bytes, vals: dict):
+    try:
+        import h5py
+    except ImportError:
+        h5py = None
+    if h5py is not None:
+        with h5py.File(filename, 'w', libver='latest') as f:
+            for k, v in vals.items():
+                f[k] = v
+            f.attrs['name'] = name
+            f.attrs['args_and_kwargs'] = np.void(blob)
+    else:
+        np.savez(filename + ".npz", __name__=name, __args__=np.frombuffer(blob, dtype=np.uint8), **vals)
+
+
+def _read_snapshot(filename):
+    """-> (class name, pickled (args, kwargs), {variable name: array})."""
+    import os
+    if filename.endswith(".npz") or (not os.path.exists(filename) and os.path.exists(filename + ".npz")):
+        data = np.load(filename if filename.endswith(".npz") else filename + ".npz", allow_pickle=False)
+        vals = {k: data[k] for k in data.files if not k.startswith("__")}
+        return str(data["__name__"]), data["__args__"].tobytes(), vals
+    import h5py   # a real HDF5 snapshot (e.g. written by the reference) needs h5py; fail loudly without it
+    vals = {}
+    with h5py.File(filename, 'r') as f:
+        f.visititems(lambda n, obj: vals.__setitem__(n, obj[...]) if isinstance(obj, h5py.Dataset) else None)
+        blob = f.attrs['args_and_kwargs'].tobytes()
+        name = f.attrs['name']
+    return (name.decode() if isinstance(name, bytes) else str(name)), blob, vals

@@ -215,3 +215,70 @@ def test_policy_reinitialize_matches_oracle():
         np.testing.assert_allclose(got, want, rtol=2e-6, atol=1e-7)
     with pytest.raises(AttributeError):
         policies.reinitialize_flat(nets.make_net("ESAtariPolicy"), torch.zeros(nets.make_net("ESAtariPolicy").num_params))
+
+
+def _cpu_policy_shell(cls, net):
+    """A Policy object without a CUDA context: enough state for the host-side snapshot / flat-vector plumbing."""
+    import torch
+    p = object.__new__(cls)
+    p.args, p.kwargs = (), {}
+    p.net, p.num_params = net, net.num_params
+    p.hidden_dims = [l.cout for l in net.layers[:-1]]          # MujocoPolicy names its layers l0..l{n-1}, out
+    p.trainable_variables = p._variable_table()
+    p.all_variables = list(p.trainable_variables)
+    p.device = torch.device("cpu")
+    p._theta = torch.zeros(net.num_params)
+    p.ob_mean = p.ob_std = None
+    return p
+
+
+def test_snapshot_roundtrip_set_all_vars_and_initialize_from(tmp_path):
+    """policies.py:36-40,49-67,219-249: variable-name keyed snapshot, set_all_vars order, growing initialize_from."""
+    from es_distributed import policies as PO
+    from es_distributed.es import RunningStat
+    from dne import nets
+    rs = np.random.RandomState(0)
+    small = _cpu_policy_shell(PO.MujocoPolicy, nets.make_net("MujocoPolicy", ob_dim=5, hidden=(8, 8), ac_dim=3))
+    small.set_trainable_flat(rs.randn(small.num_params).astype(np.float32))
+    small.set_ob_stat(rs.randn(5).astype(np.float32), np.abs(rs.randn(5)).astype(np.float32) + 0.5)
+    fn = str(tmp_path / "snap.h5")
+    small.save(fn)
+    name, blob, data = PO._read_snapshot(fn)
+    assert name == "MujocoPolicy" and set(data) == {n for n, _, _ in small.all_variables} | {"MujocoPolicy/ob_mean:0", "MujocoPolicy/ob_std:0"}
+    for n, shp, off in small.all_variables:
+        assert data[n].shape == tuple(shp)
+        np.testing.assert_array_equal(data[n].reshape(-1), small.get_trainable_flat()[off:off + data[n].size])
+    # set_all_vars: all_variables order
+    twin = _cpu_policy_shell(PO.MujocoPolicy, small.net)
+    twin.set_all_vars(*[data[n] for n, _, _ in twin.all_variables])
+    np.testing.assert_array_equal(twin.get_trainable_flat(), small.get_trainable_flat())
+    with pytest.raises(AssertionError):
+        twin.set_all_vars(*[data[n] for n, _, _ in twin.all_variables][:-1])
+    # initialize_from into a wider policy: leading sub-arrays filled, the rest untouched; ob stat -> RunningStat
+    big = _cpu_policy_shell(PO.MujocoPolicy, nets.make_net("MujocoPolicy", ob_dim=5, hidden=(16, 16), ac_dim=3))
+    base = rs.randn(big.num_params).astype(np.float32)
+    big.set_trainable_flat(base.copy())
+    st = RunningStat((5,), eps=1e-2)
+    big.initialize_from(fn, ob_stat=st)
+    got = big.get_trainable_flat()
+    for (n, shp, off), (_, sshp, _) in zip(big.all_variables, small.all_variables):
+        cur = got[off:off + int(np.prod(shp))].reshape(shp)
+        ref = base[off:off + int(np.prod(shp))].reshape(shp).copy()
+        ref[tuple(np.s_[:k] for k in sshp)] = data[n]
+        np.testing.assert_array_equal(cur, ref)
+    np.testing.assert_allclose(st.mean, data["MujocoPolicy/ob_mean:0"], rtol=1e-6)
+    np.testing.assert_allclose(big.ob_mean.numpy(), data["MujocoPolicy/ob_mean:0"])
+    other = _cpu_policy_shell(PO.LargeModelPolicy, nets.make_net("LargeModel"))
+    with pytest.raises(AssertionError):
+        other.initialize_from(fn)
+
+
+def test_get_ref_batch_host_env():
+    """es.py:105-113 on the batched host env: `batch_size` frames, uint8 84x84x4, copies (not views of the pool)."""
+    from dne.envs import SyntheticAtariEnv
+    from es_distributed import es
+    env = SyntheticAtariEnv(2, episode_len=3, seed=0, pin=False)
+    rb = es.get_ref_batch(env, batch_size=5)
+    assert len(rb) == 5 and all(f.shape == (84, 84, 4) and f.dtype == np.uint8 for f in rb)
+    rb[0][:] = 7
+    assert not np.all(env.pool.numpy()[:, 0] == 7)
