@@ -4,12 +4,16 @@
 //   A[m][k] = im2col(input)            m = output position, k = (ky,kx,ci)      (TF SAME, NHWC)
 //   B[n][k] = theta_w[k][n] + s*noise[idx+off_w+k*COUT+n]   (member weights, built by the perturb stage)
 //   D[m][n] = sum_k A*B  -> +bias (+virtual BN) -> relu -> NHWC store
-// fp32 parity on tensor cores: 3xTF32 -- every operand is split into hi + lo TF32 halves by the staging threads
-// (round-to-nearest, so the hardware's fp32->tf32 truncation is exact) and D += Ahi*Bhi + Alo*Bhi + Ahi*Blo.
+// fp32 parity on tensor cores: 3xTF32 -- operands are split into hi + lo TF32 parts by the staging threads (hi rounded to
+// nearest, so the hardware's fp32->tf32 truncation of hi is exact; lo = x - hi is truncated by the hardware) and
+// D = Ahi*Bhi + Alo*Bhi + Ahi*Blo.  B_hi and B_lo are stacked along N in one tile, so Ahi*[Bhi;Blo] is ONE MMA (N = 2*COUT)
+// and Alo*Bhi a second one; uint8 inputs are staged as exact integers (no lo plane, /255 in the epilogue).
 // Operands are PRODUCED into shared memory by the perturb / im2col stage (they do not exist in global memory, so
 // there is nothing for TMA to fetch); the layout is the UMMA K-major no-swizzle canonical layout (tc05.cuh).
-// One thread issues the MMAs of k-chunk c while all threads stage chunk c+1 (two smem stages, mbarrier-tracked by
-// tcgen05.commit); the 8 warps then drain TMEM with tcgen05.ld for the fused epilogue.
+// Warp-specialised mbarrier pipeline, no block barriers in the loop: TC_GROUPS staging groups of 128 threads (group g
+// owns shared-memory stage g and the k-chunks c = g mod TC_GROUPS) + one MMA warp that runs converged and issues from one
+// elected lane (tc05.cuh: elect_one); stage hand-off full[g] (staging warps arrive) / empty[g] (tcgen05.commit).
+// The staging warps then drain TMEM with tcgen05.ld for the fused epilogue.
 #include "common.cuh"
 #include "forward.cuh"
 #include "epilogue.cuh"
