@@ -139,3 +139,71 @@ def test_novelty():
     nov = O.compute_novelty_vs_archive(arch, q, k=2)
     d = sorted(O.euclidean_distance(a.astype(np.float64), q.astype(np.float64)) for a in arch)
     assert nov == pytest.approx((d[0] + d[1]) / 2)
+
+
+# ---- size-independent properties (hypothesis): the same properties the GPU suite checks at BASELINE sizes ----------
+from hypothesis import given, settings, strategies as st   # noqa: E402
+from hypothesis.extra import numpy as hnp                  # noqa: E402
+
+_f32s = st.floats(min_value=-1e4, max_value=1e4, allow_nan=False, width=32)
+
+
+@settings(max_examples=60, deadline=None)
+@given(hnp.arrays(np.float32, st.integers(2, 200), elements=_f32s))
+def test_ranks_are_the_stable_sort_permutation(x):
+    r = O.compute_ranks(x)
+    assert sorted(r.tolist()) == list(range(len(x)))                      # a permutation of 0..n-1
+    order = np.argsort(x, kind="stable")
+    np.testing.assert_array_equal(r[order], np.arange(len(x)))           # rank of the i-th smallest is i; ties by index
+    c = O.compute_centered_ranks(x)
+    assert c.dtype == np.float32 and c.min() == np.float32(-0.5) and c.max() == np.float32(0.5)
+    y = x * np.float32(3.0) + np.float32(1.0)                            # es.py:77 is invariant under order-preserving maps
+    if np.unique(y).size == np.unique(x).size:                           # (unless float32 rounding merged two values)
+        np.testing.assert_array_equal(O.compute_ranks(y), r)
+
+
+@settings(max_examples=30, deadline=None)
+@given(st.integers(1, 12), st.integers(1, 40), st.integers(0, 2 ** 31 - 1))
+def test_es_gradient_linearity_and_antithetic_cancellation(n, dim, seed):
+    rs = np.random.RandomState(seed)
+    noise = rs.randn(4096).astype(np.float32)
+    idx = rs.randint(0, len(noise) - dim + 1, size=n)
+    a = rs.randn(n, 2).astype(np.float32)
+    b = rs.randn(n, 2).astype(np.float32)
+    ga, gb = O.es_gradient(a, noise, idx, dim), O.es_gradient(b, noise, idx, dim)
+    gab = O.es_gradient((a.astype(np.float64) + 2.0 * b).astype(np.float64), noise, idx, dim)
+    np.testing.assert_allclose(gab, ga + 2.0 * gb, rtol=1e-5, atol=1e-6)
+    same = np.repeat(a[:, :1], 2, axis=1)                                 # w+ == w-  ->  zero gradient (es.py:292)
+    assert np.all(O.es_gradient(same, noise, idx, dim) == 0)
+    # batched_weighted_sum in slabs == one slab (es.py:115-122) up to float32 re-association
+    w = (a[:, 0] - a[:, 1]).astype(np.float32)
+    s1 = O.batched_weighted_sum(w, noise, idx, dim, batch_size=3)
+    s2 = O.batched_weighted_sum(w, noise, idx, dim, batch_size=500)
+    np.testing.assert_allclose(s1, s2, rtol=1e-4, atol=1e-4)
+
+
+@settings(max_examples=60, deadline=None)
+@given(hnp.arrays(np.float32, st.integers(1, 120), elements=st.sampled_from([0.0, 10.0, 20.0, 30.0, -10.0, 7.5])), st.data())
+def test_ga_truncate_is_pythons_stable_descending_sort(fit, data):
+    T = data.draw(st.integers(1, len(fit)))
+    want = sorted(range(len(fit)), key=lambda i: fit[i], reverse=True)[:T]     # gpu_implementation/ga.py:180
+    np.testing.assert_array_equal(O.ga_truncate(fit, T), want)
+
+
+@settings(max_examples=40, deadline=None)
+@given(st.integers(1, 9), st.integers(1, 9), st.integers(1, 6), st.integers(0, 2 ** 31 - 1))
+def test_bc_distance_padding_and_symmetry(n, m, d, seed):
+    rs = np.random.RandomState(seed)
+    x = rs.randint(0, 256, size=(n, d)).astype(np.float64)
+    y = rs.randint(0, 256, size=(m, d)).astype(np.float64)
+    dist = O.euclidean_distance(x, y)
+    assert dist == O.euclidean_distance(y, x) and O.euclidean_distance(x, x) == 0.0
+    L = max(n, m)                                                        # nses.py:12-20: pad the shorter with its last row
+    xp = np.concatenate([x, np.repeat(x[-1:], L - n, axis=0)])
+    yp = np.concatenate([y, np.repeat(y[-1:], L - m, axis=0)])
+    np.testing.assert_allclose(dist, np.sqrt(np.square(xp - yp).sum()), rtol=1e-12)
+    arch = [rs.randint(0, 256, size=(rs.randint(1, 9), d)).astype(np.uint8) for _ in range(5)]
+    k = 3
+    nov = O.compute_novelty_vs_archive(arch, x.astype(np.uint8), k)
+    ds = sorted(O.euclidean_distance(a.astype(np.float64), x) for a in arch)
+    np.testing.assert_allclose(nov, np.mean(ds[:k]), rtol=1e-12)
