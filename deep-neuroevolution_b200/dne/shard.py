@@ -81,6 +81,18 @@ def broadcast_seed(seed) -> int:
     return seed
 
 
+def broadcast_object(obj, src: int = 0):
+    """Rank ``src``'s picklable object on every rank (identity at world size 1).  Used for small host-side results that
+    must be IDENTICAL everywhere although every rank could recompute them (e.g. a behaviour characterisation from a
+    possibly stochastic host environment)."""
+    _, world = dist_info()
+    if world == 1:
+        return obj
+    box = [obj]
+    dist.broadcast_object_list(box, src=src)
+    return box[0]
+
+
 def barrier():
     _, world = dist_info()
     if world > 1:

@@ -86,8 +86,15 @@ def run_master(master_redis_cfg, log_dir, exp, *, max_iterations=None, n_slots=2
     from .optimizers import SGD, Adam
     from . import tabular_logger as tlogger
     rank, world = shard.dist_info()
-    assert world == 1, "nses: single-GPU driver in this round (population sharding: es.run_master)"
-    tlogger.start(log_dir)
+    # Multi-GPU: rollout units sharded over the ranks; every rank scores its own BCs against the (replicated)
+    # archive and the ranks all_gather (returns, lengths, novelty) -- a few floats per pair instead of the BC traces --
+    # then the ES collectives (partial gradient with the global denominator, one all_reduce).  Everything that feeds the
+    # archive or the parent choice comes from rank 0 (broadcast), so the replicas cannot drift apart.
+    # world == 1 executes exactly the single-GPU statements.  NOTE: the world > 1 path has not yet been run on >1 GPU.
+    if rank == 0:
+        tlogger.start(log_dir)
+    else:
+        tlogger.set_quiet(True)
     if noise is not None:
         set_default_noise(noise)
     noise = default_noise()
@@ -118,7 +125,7 @@ def run_master(master_redis_cfg, log_dir, exp, *, max_iterations=None, n_slots=2
         opt = {'sgd': SGD, 'adam': Adam}[exp['optimizer']['type']](pol_p.get_trainable_flat(), ctx=ctx,
                                                                    **exp['optimizer']['args'])
         theta_dict[p], optimizer_dict[p] = opt.device_theta, opt
-        archive.append(mean_bc(opt.device_theta))
+        archive.append(shard.broadcast_object(mean_bc(opt.device_theta)))
 
     curr_parent = 0
     episodes_so_far = timesteps_so_far = 0
@@ -133,17 +140,24 @@ def run_master(master_redis_cfg, log_dir, exp, *, max_iterations=None, n_slots=2
         idx = np.array([noise.sample_index(rs, P) for _ in range(n_pairs)], dtype=np.int64)
         sig = np.float32(config.noise_stdev)
         units = [Unit(int(i), (sig, -sig)) for i in idx]
-        res = runner.run(optimizer.device_theta, units, tslimit, collect_bc="trace")
-        bcs = [res.bcs[u][g] for u in range(n_pairs) for g in range(2)]
-        novelty_n2 = compute_novelty_vs_archive(archive, bcs, k).reshape(n_pairs, 2).astype(np.float32)   # nses.py:381-384
+        lo, hi = shard.shard_bounds(n_pairs, rank, world)
+        res = runner.run(optimizer.device_theta, units[lo:hi], tslimit, collect_bc="trace")
+        bcs = [res.bcs[u][g] for u in range(hi - lo) for g in range(2)]
+        novelty_n2 = compute_novelty_vs_archive(archive, bcs, k).reshape(hi - lo, 2).astype(np.float32)   # nses.py:381-384
         returns_n2, lengths_n2 = res.returns, res.lengths
+        if world > 1:
+            pack = torch.from_numpy(np.concatenate([returns_n2, lengths_n2.astype(np.float32), novelty_n2], axis=1)).to(dev)
+            allr = shard.all_gather_rows(pack, n_pairs).cpu().numpy()
+            returns_n2, lengths_n2 = allr[:, 0:2].astype(np.float32), allr[:, 2:4].astype(np.int32)
+            novelty_n2 = allr[:, 4:6].astype(np.float32)
         proc = _process_returns(config, upd, torch.from_numpy(returns_n2).to(dev), torch.from_numpy(novelty_n2).to(dev))
         if algo_type == "nsr":                                                                         # nses.py:226-228
             rew_ranks = upd.centered_ranks(torch.from_numpy(returns_n2).to(dev))[0]
             proc = (rew_ranks + proc) / 2.0
-        g = upd.gradient(proc.contiguous(), torch.from_numpy(idx).to(dev), denom=returns_n2.size)
+        g = upd.gradient(proc[lo:hi].contiguous(), torch.from_numpy(idx[lo:hi]).to(dev), denom=returns_n2.size)
+        shard.all_reduce_sum_(g)
         update_ratio, _ = optimizer.update_from_gradient(g, config.l2coeff)
-        archive.append(mean_bc(optimizer.device_theta))                                                # nses.py:246-247
+        archive.append(shard.broadcast_object(mean_bc(optimizer.device_theta)))                        # nses.py:246-247
         if adaptive and (lengths_n2 == tslimit).mean() >= incr_thr:
             tslimit = min(int(incr_ratio * tslimit), tslimit_max)
         episodes_so_far += lengths_n2.size
@@ -155,9 +169,10 @@ def run_master(master_redis_cfg, log_dir, exp, *, max_iterations=None, n_slots=2
                      EpisodesSoFar=int(episodes_so_far), TimestepsThisIter=int(lengths_n2.sum()),
                      TimestepsSoFar=int(timesteps_so_far), ArchiveSize=len(archive),
                      TimeElapsedThisIter=time.time() - step_tstart, TimeElapsed=time.time() - tstart)
-        for kk, v in stats.items():
-            tlogger.record_tabular(kk, v)
-        tlogger.dump_tabular()
+        if rank == 0:
+            for kk, v in stats.items():
+                tlogger.record_tabular(kk, v)
+            tlogger.dump_tabular()
         if on_iteration is not None:
             on_iteration(it, stats, dict(noise_inds_n=idx, returns_n2=returns_n2, novelty_n2=novelty_n2, g=g, bcs=bcs,
                                          archive=archive, parent=curr_parent, theta=optimizer.device_theta))
@@ -165,7 +180,7 @@ def run_master(master_redis_cfg, log_dir, exp, *, max_iterations=None, n_slots=2
         if ns['selection_method'] == "novelty_prob":
             nov = compute_novelty_vs_archive(archive, [mean_bc(theta_dict[p]) for p in range(pop_size)], k).astype(np.float64)
             probs = nov / float(nov.sum()) if nov.sum() > 0 else np.full(pop_size, 1.0 / pop_size)
-            curr_parent = int(rs.choice(range(pop_size), 1, p=probs)[0])
+            curr_parent = int(shard.broadcast_object(int(rs.choice(range(pop_size), 1, p=probs)[0])))
         elif ns['selection_method'] == "round_robin":
             curr_parent = (curr_parent + 1) % pop_size
         else:

@@ -133,6 +133,10 @@ g = torch.from_numpy((part / allr.size).astype(np.float32))
 shard.all_reduce_sum_(g)
 ref = O.es_gradient(proc, noise, idx, P, dtype=np.float64)
 assert np.abs(g.numpy() - ref).max() <= 1e-5 * np.abs(ref).max()
+# rank 0's host-side object everywhere (the NS-ES archive entries / parent choice use it)
+bc = shard.broadcast_object(np.arange(12, dtype=np.uint8).reshape(3, 4) + 7 if rank == 0 else None)
+assert bc.dtype == np.uint8 and bc.shape == (3, 4) and int(bc[0, 0]) == 7
+assert shard.broadcast_object(41 + rank) == 41
 shard.barrier()
 if rank == 0:
     print("GLOO_OK", seed)
