@@ -299,6 +299,9 @@ def run_b200(args):
                         "survey_bytes = SURVEY 8d figure (4P + obs + action per env-step, every member its own slice). "
                         "~5% of the slice bytes hit in L2 (random 16 MB slices of a 1 GB table overlap), hence frac > 1."}
 
+    # ------------------------------------------------------------------ output check of the benchmarked kernels
+    parity = parity_check(L, ctx, net, sfs[0], upd.theta, obs_ptr[0][0], pool[0][:part], part)
+
     # ------------------------------------------------------------------ e2e: public API, host environment
     e2e = None
     if not args.no_e2e:
@@ -352,12 +355,53 @@ def run_b200(args):
                        "l2": "inputs larger than L2 (>=1 GB of noise slices streamed per tick)",
                        "step": "one generation (rollouts + update)"},
             "generation_wall_clock_s": ms_val / args.steps / 1e3,
+            "parity_checked": bool(parity and parity["checked"]), "parity": parity,
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
             "noise_table_build_s": t_noise,
         }
         _emit(line)
     if world > 1:
         dist.destroy_process_group()
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def parity_check(L, ctx, net, sf, theta, obs_p, obs, n_slots):
+    """After the timed region: one tick of the benchmarked slot table (whatever indices / active mask the last wave
+    left in it) through the benchmarked kernels (tcgen05 convolutions + TMA bulk-copy GEMV) and through the plain fp32
+    SIMT kernels (dne_set_option conv_tc = 0, gemv_bulk = 0; same C ABI, no oracle involved): logits within twice the
+    forward bound of tests/test_gpu_parity.py on every active slot, identical actions wherever the top-2 gap decides."""
+    import ctypes as C
+    import torch
+    from dne import _ffi as F
+
+    def one(fast):
+        F.check(L.dne_set_option(b"conv_tc", fast))
+        F.check(L.dne_set_option(b"gemv_bulk", fast))
+        sf.logits.fill_(0)
+        sf.actions.fill_(-1)
+        F.check(L.dne_perturb_forward_conv(ctx.handle, C.byref(net.desc), F.ptr(theta), F.ptr(sf.noise_idx), F.ptr(sf.scale),
+                                           None, F.ptr(sf.active), n_slots, 1, obs_p, None, F.ptr(sf.actions),
+                                           F.ptr(sf.logits), F.ptr(sf.ws), sf.ws.numel(), F.stream_ptr()))
+        torch.cuda.synchronize()
+        return sf.logits.clone(), sf.actions.clone()
+    try:
+        lf, af = one(1)
+        ls, as_ = one(0)
+    finally:
+        L.dne_set_option(b"conv_tc", 1)
+        L.dne_set_option(b"gemv_bulk", 1)
+    act = sf.active.bool() if sf.active is not None else torch.ones(n_slots, dtype=torch.bool, device=lf.device)
+    lf, ls, af, as_ = lf[act], ls[act], af[act], as_[act]
+    bound = 4e-5 * torch.clamp(ls.abs().max(dim=1).values, min=1.0)
+    err = (lf - ls).abs().max(dim=1).values
+    srt = ls.sort(dim=1).values
+    decided = (srt[:, -1] - srt[:, -2]) > 2 * bound
+    ok = bool((err <= bound).all()) and bool(torch.equal(af[decided], as_[decided])) and bool(torch.isfinite(lf).all())
+    if not ok:
+        raise RuntimeError(f"bench parity check failed: max |dlogit| {float(err.max()):.3e} (bound {float(bound.min()):.3e})")
+    return {"checked": True, "slots": int(act.sum()), "max_abs_dlogit": float(err.max()), "bound": float(bound.min()),
+            "decided_frac": float(decided.float().mean()),
+            "against": "fp32 SIMT kernels of the same library (conv_tc=0, gemv_bulk=0) on the benchmarked slot table"}
 
 
 # ---------------------------------------------------------------------------------------------------------------

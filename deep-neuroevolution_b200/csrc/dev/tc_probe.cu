@@ -3,8 +3,8 @@
 // layout 0: K-major no-swizzle (interleave): float4 T[KC/4][rows]           (LBO = rows*16, SBO = 128)
 // layout 1: K-major SWIZZLE_32B : 8-row x 32 B atoms, k-block stride rows*32 (SBO = 256)
 // layout 2: K-major SWIZZLE_128B: 8-row x 128 B atoms (KC = 32 per row)      (SBO = 1024), K advance = +32 B
-#include "common.cuh"
-#include "tc05.cuh"
+#include "dev.cuh"
+#include "../tc05.cuh"
 using namespace tc05;
 
 __device__ __forceinline__ uint64_t desc_layout(uint32_t saddr, uint32_t lbo, uint32_t sbo, uint32_t layout_type) {

@@ -63,8 +63,6 @@ _SIGS = {
     "dne_abi_sizes": [C.POINTER(C.c_int), C.POINTER(C.c_int)],
     "dne_set_option": [C.c_char_p, C.c_int],
     "dne_set_phase_events": [_P, _P, _P, C.c_int],
-    "dne_test_tc_gemm": [_P, _P, _P, C.c_int, C.c_int, _P],
-    "dne_probe_mma": [_P, _P, _P, C.c_int, C.c_int, C.c_int, _P, _P],
     "dne_profile_enable": [_P, C.c_int, C.c_int],
     "dne_profile_read": [_P, C.POINTER(C.c_int), C.POINTER(C.c_double)],
     "dne_ga_mutate": [_P, _P, C.c_int64, C.c_float, C.c_int64, _P, _P],
@@ -99,6 +97,31 @@ def lib():
             raise DneError(f"ABI mismatch: C structs {a.value}/{b.value} bytes, ctypes {C.sizeof(LayerDesc)}/{C.sizeof(NetDesc)}")
         _lib = L
     return _lib
+
+
+_DEV_SIGS = {
+    "dne_test_tc_gemm": [_P, _P, _P, C.c_int, C.c_int, _P],
+    "dne_probe_mma": [_P, _P, _P, C.c_int, C.c_int, C.c_int, _P, _P],
+    "dne_dev_tc_window": [_P, _P, _P, C.c_int, C.c_int, C.POINTER(C.c_int), C.c_int, C.c_int, C.c_int, C.c_int, _P],
+}
+_dev = None
+
+
+def dev_lib():
+    """libdne_dev.so: self-tests / micro-probes of the tcgen05 + TMA plumbing (csrc/dev/).  Tests and tools only; the
+    product path never loads it."""
+    global _dev
+    if _dev is None:
+        path = os.path.join(_HERE, "libdne_dev.so")
+        if not os.path.exists(path):
+            raise DneError(f"{path} not built (make -C csrc)")
+        L = C.CDLL(path)
+        for name, args in _DEV_SIGS.items():
+            fn = getattr(L, name)
+            fn.argtypes = args
+            fn.restype = C.c_int
+        _dev = L
+    return _dev
 
 
 def check(rc: int):

@@ -98,14 +98,6 @@ long long   dne_launch_count(int reset);
  *   "gemv_ctas_per_sm" = 1|2 (default 2), "gemv_stages" = 2..8 (default 6): persistent-grid size / ring depth of it.
  *   "gemv_prefetch" = 0..256 (default 0): L2 prefetch distance in 16 KB stages (measured slower on B200; off). */
 int         dne_set_option(const char* name, int value);
-/* Self-test of the tcgen05 plumbing: C[128,N] = A[128,K] * B[N,K]^T (row-major, K % 32 == 0, N in {16,32,64}). */
-int         dne_test_tc_gemm(const float* d_A, const float* d_B, float* d_C, int K, int N, void* stream);
-/* Micro-probe of tcgen05.mma kind::tf32 (tools/probe_mma.py): one CTA, A [128,32] / B [N,32] row-major staged once,
- * `reps` batches of MMAs accumulated; d_cycles[0] = clock64 ticks of the batch.  layout = smem operand layout
- * (0 no-swizzle, 1 SWIZZLE_32B, 2 SWIZZLE_128B) | mode << 4 (0 chain, 1 commit+wait per 6 MMAs, 2/3 chain under
- * generic / st.shared store traffic, 4 full/empty ping-pong with a staging warp). */
-int         dne_probe_mma(const float* d_A, const float* d_B, float* d_C, int N, int layout, int reps,
-                          long long* d_cycles, void* stream);
 int         dne_profile_enable(dne_ctx* ctx, int on, int capacity);
 int         dne_profile_read(dne_ctx* ctx, int* n_launches, double* total_ms);
 

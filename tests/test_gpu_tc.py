@@ -43,7 +43,7 @@ def test_tcgen05_gemm_selftest(n, k):
     B = rs.randn(n, k).astype(np.float32)
     dA, dB = cuda(A), cuda(B)
     dC = torch.full((128, n), float("nan"), dtype=torch.float32, device=DEV)
-    F.check(F.lib().dne_test_tc_gemm(F.ptr(dA), F.ptr(dB), F.ptr(dC), k, n, F.stream_ptr()))
+    F.check(F.dev_lib().dne_test_tc_gemm(F.ptr(dA), F.ptr(dB), F.ptr(dC), k, n, F.stream_ptr()))
     got = dC.cpu().numpy()
     ref = A.astype(np.float64) @ B.astype(np.float64).T
     scale = np.abs(ref).max()
@@ -168,3 +168,37 @@ def test_two_tables_with_phase_events_match_single_table(ctx, host_noise):
         got = torch.cat([tabs[0].logits, tabs[1].logits])
         assert torch.equal(got, ref_logits), mode
         assert torch.equal(torch.cat([tabs[0].actions, tabs[1].actions]), ref_actions)
+
+
+@pytest.mark.parametrize("use_tma", [0, 1])
+@pytest.mark.parametrize("C_,pixp,W,taps,N,row0", [
+    (16, 144, 12, [(0, 0), (0, 1), (1, 0), (1, 1)], 64, 0),      # conv2 geometry: 12-wide s2d grid, LBO 2304 B
+    (16, 144, 12, [(0, 0), (0, 1), (1, 0), (1, 1)], 128, 3),     # second tile starting at an arbitrary (16 B aligned) row
+    (16, 176, 13, [(dy, dx) for dy in range(3) for dx in range(3)], 128, 0),   # conv3 geometry: 13-wide grid, 9 taps
+    (8, 169, 13, [(dy, dx) for dy in range(3) for dx in range(3)], 64, 13),    # LBO 2704 B: NOT a multiple of 128 B
+    (16, 488, 22, [(0, 0), (0, 1), (1, 0), (1, 1)], 64, 256),    # conv1 geometry: 22-wide grid, third M tile
+])
+def test_tcgen05_shifted_window_operand(C_, pixp, W, taps, N, row0, use_tma):
+    """The A operand of the convolution kernels: channel-quad planes of an activation image addressed through a
+    descriptor whose start address is shifted by (dy*W + dx) pixels (16 bytes each) per filter tap -- no im2col copy.
+    Exact integer data, so the tensor-core result must equal the reference bit for bit."""
+    rs = np.random.RandomState(C_ * 1000 + pixp + N + row0)
+    img = rs.randint(-8, 9, size=(C_ // 4, pixp, 4)).astype(np.float32)
+    K = len(taps) * C_
+    Bw = rs.randint(-4, 5, size=(N, K)).astype(np.float32)
+    off = np.array([dy * W + dx for dy, dx in taps], dtype=np.int32)
+    d_img, d_B = cuda(img), cuda(Bw)
+    d_D = torch.full((128, N), float("nan"), dtype=torch.float32, device=DEV)
+    F.check(F.dev_lib().dne_dev_tc_window(F.ptr(d_img), F.ptr(d_B), F.ptr(d_D), C_, len(taps),
+                                          off.ctypes.data_as(C.POINTER(C.c_int)), pixp, N, row0, use_tma, F.stream_ptr()))
+    got = d_D.cpu().numpy()
+    flat = img.transpose(1, 0, 2).reshape(pixp, C_)                  # [pixel][channel]
+    ref = np.zeros((128, N), dtype=np.float64)
+    valid = np.ones(128, dtype=bool)
+    for t, o in enumerate(off):
+        rows = row0 + np.arange(128) + o
+        ok = rows < pixp                                            # rows past the image read other planes / slack: ignored
+        valid &= ok
+        ref[ok] += flat[rows[ok]].astype(np.float64) @ Bw[:, t * C_:(t + 1) * C_].astype(np.float64).T
+    assert valid.sum() >= 32
+    np.testing.assert_array_equal(got[valid], ref[valid].astype(np.float32))

@@ -4,7 +4,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "deep-neuroevolution_b200")]
 import numpy as np, torch
 from dne import _ffi as F
-L = F.lib()
+L = F.dev_lib()
 rs = np.random.RandomState(0)
 cyc = torch.zeros(1, dtype=torch.int64, device="cuda")
 names = {0: "chain (4 MMAs/iter)", 1: "6 MMAs + commit + wait / iter", 2: "chain + generic ST traffic (3 warps)",
