@@ -375,7 +375,7 @@ def parity_check(L, ctx, net, sf, theta, obs_p, obs, n_slots):
     from dne import _ffi as F
 
     def one(fast):
-        F.check(L.dne_set_option(b"conv_tc", fast))
+        F.check(L.dne_set_option(b"conv_tc", 2 if fast else 0))
         F.check(L.dne_set_option(b"gemv_bulk", fast))
         sf.logits.fill_(0)
         sf.actions.fill_(-1)
@@ -388,7 +388,7 @@ def parity_check(L, ctx, net, sf, theta, obs_p, obs, n_slots):
         lf, af = one(1)
         ls, as_ = one(0)
     finally:
-        L.dne_set_option(b"conv_tc", 1)
+        L.dne_set_option(b"conv_tc", 2)
         L.dne_set_option(b"gemv_bulk", 1)
     act = sf.active.bool() if sf.active is not None else torch.ones(n_slots, dtype=torch.bool, device=lf.device)
     lf, ls, af, as_ = lf[act], ls[act], af[act], as_[act]

@@ -4,6 +4,7 @@
 
 static thread_local char g_err[512] = "";
 unsigned long long g_dne_launches = 0;
+int g_dne_fuse_head = 1;     // combine + output head in one kernel (dne_set_option("fuse_head", v))
 
 void dne_set_error(const char* fmt, ...) {
     va_list ap;
@@ -70,8 +71,9 @@ extern "C" int dne_ctx_destroy(dne_ctx* ctx) {
 // Runtime switches: "conv_tc" (1 = tcgen05 convolutions [default], 0 = fp32 SIMT convolutions).
 extern "C" int dne_set_option(const char* name, int value) {
     DNE_CHECK_ARG(name, "name is null");
-    if (strcmp(name, "conv_tc") == 0) { g_dne_conv_tc = value ? 1 : 0; return DNE_OK; }
+    if (strcmp(name, "conv_tc") == 0 && value >= 0 && value <= 2) { g_dne_conv_tc = value; return DNE_OK; }
     if (strcmp(name, "gemv_bulk") == 0) { g_dne_gemv_bulk = value ? 1 : 0; return DNE_OK; }
+    if (strcmp(name, "fuse_head") == 0) { g_dne_fuse_head = value ? 1 : 0; return DNE_OK; }
     if (strcmp(name, "gemv_stages") == 0 && value >= 2 && value <= 8) { extern int g_dne_gemv_stages; g_dne_gemv_stages = value; return DNE_OK; }
     if (strcmp(name, "gemv_prefetch") == 0 && value >= 0 && value <= 256) { extern int g_dne_gemv_prefetch; g_dne_gemv_prefetch = value; return DNE_OK; }
     if (strcmp(name, "gemv_ctas_per_sm") == 0 && value >= 1 && value <= 2) { g_dne_gemv_ctas_per_sm = value; return DNE_OK; }
@@ -157,6 +159,12 @@ static int plan_forward(const dne_net_desc* net, int n_slots, int paired, bool s
     for (int l = 0; l < net->n_layers; ++l) {
         const dne_layer_desc& L = net->layers[l];
         fp->act_elems[l] = layer_out_elems(L);
+        // conv -> conv hand-off of the s2d path: the producing epilogue writes the NEXT layer's image (space-to-depth,
+        // zero padded, TF32 hi/lo planes: conv_s2d.cu), which is larger than the NHWC activation
+        if (L.kind == DNE_CONV && l + 1 < net->n_layers && net->layers[l + 1].kind == DNE_CONV) {
+            const int64_t img = (int64_t)(dne_s2d_image_bytes(net->layers[l + 1]) / sizeof(float));
+            if (img > fp->act_elems[l]) fp->act_elems[l] = img;
+        }
         fp->act_off[l] = off;
         off += align_up((size_t)n_slots * fp->act_elems[l] * sizeof(float), 256);
         if (L.kind == DNE_DENSE) {
@@ -188,6 +196,19 @@ extern "C" int dne_forward_ws_bytes(const dne_net_desc* net, int n_slots, size_t
     return DNE_OK;
 }
 
+static LayerEpi make_layer_epi(const dne_layer_desc& L, const dne_net_desc* net, const float* d_vbn) {
+    LayerEpi epi;
+    epi.off_b = L.off_b;
+    epi.off_beta = L.off_beta;
+    epi.off_gamma = L.off_gamma;
+    epi.act = L.act;
+    epi.bn = L.bn;
+    epi.bn_off = L.bn_off;
+    epi.vbn_len = net->vbn_len;
+    epi.vbn = d_vbn;
+    return epi;
+}
+
 static int forward_impl(dne_ctx* ctx, const dne_net_desc* net, const float* d_theta, const int64_t* d_noise_idx,
                         const float* d_scale, const int32_t* d_theta_idx, const uint8_t* d_active, int n_slots,
                         int paired, const void* d_obs, const float* d_ob_mean, const float* d_ob_std,
@@ -201,6 +222,9 @@ static int forward_impl(dne_ctx* ctx, const dne_net_desc* net, const float* d_th
     DNE_CHECK_ARG(paired != 2 || d_theta_idx, "paired == 2 needs d_theta_idx");
     DNE_CHECK_ARG(net->num_params <= ctx->noise_count, "net larger than the noise table");
     DNE_CHECK_ARG(((uintptr_t)d_ws & 255) == 0, "workspace must be 256-byte aligned");
+    // the GEMV / conv kernels derive 16-byte alignment of their vector and bulk loads from element indices relative to
+    // the theta BASE pointer (rows of a [n_theta, P] matrix may start anywhere: P % 4 != 0 is handled)
+    DNE_CHECK_ARG(((uintptr_t)d_theta & 15) == 0, "d_theta must be 16-byte aligned (pass the base of the parameter matrix, not a row view)");
     if (n_slots == 0) return DNE_OK;
     ForwardPlan fp;
     int rc = plan_forward(net, n_slots, paired, d_theta_idx == nullptr, &fp);
@@ -213,6 +237,11 @@ static int forward_impl(dne_ctx* ctx, const dne_net_desc* net, const float* d_th
     for (int l = 0; l < net->n_layers; ++l) needs_vbn = needs_vbn || (net->layers[l].bn == DNE_BN_TF);
     DNE_CHECK_ARG(!needs_vbn || d_vbn, "net has batch-norm layers: d_vbn (dne_vbn_reference_pass) required");
 
+    // conv path: 2 = shifted-window kernels with TMA-fed images between the conv layers (conv_s2d.cu) when every conv
+    // layer of the net has a compiled shape; 1 = per-member im2col staging (tc_conv.cu); 0 = fp32 SIMT
+    bool use_s2d = (g_dne_conv_tc >= 2) && net->ob_kind == DNE_OB_ATARI_U8;
+    for (int l = 0; l < net->n_layers && use_s2d; ++l)
+        if (net->layers[l].kind == DNE_CONV) use_s2d = dne_s2d_supported(net->layers[l], l == 0);
     cudaStream_t st = (cudaStream_t)stream;
     // phase events (dne_set_phase_events): consumed by this call
     if (ctx->ev_wait && ctx->ev_mode == 0) {
@@ -231,7 +260,8 @@ static int forward_impl(dne_ctx* ctx, const dne_net_desc* net, const float* d_th
     sa.P = net->num_params;
 
     const void* cur = d_obs;
-    int64_t cur_elems = net->ob_dim;
+    int64_t cur_elems = net->ob_dim;           // logical elements per slot of the current activation ...
+    int64_t cur_stride = net->ob_dim;          // ... and the slot stride of the buffer that holds it
     bool cur_u8 = (net->ob_kind == DNE_OB_ATARI_U8);
     if (net->ob_kind == DNE_OB_VECTOR) {
         float* x0 = (float*)(ws + fp.x0_off);
@@ -240,7 +270,7 @@ static int forward_impl(dne_ctx* ctx, const dne_net_desc* net, const float* d_th
         DNE_LAUNCH_CHECK();
         cur = x0;
     } else {
-        cur_elems = 84 * 84 * 4;
+        cur_elems = cur_stride = 84 * 84 * 4;
     }
     for (int l = 0; l < net->n_layers; ++l) {
         const dne_layer_desc& L = net->layers[l];
@@ -248,18 +278,18 @@ static int forward_impl(dne_ctx* ctx, const dne_net_desc* net, const float* d_th
         float* out = (float*)(ws + fp.act_off[l]);
         int64_t out_stride = fp.act_elems[l];
         if (last && d_out) { out = d_out; out_stride = net->n_out; }
-        LayerEpi epi;
-        epi.off_b = L.off_b;
-        epi.off_beta = L.off_beta;
-        epi.off_gamma = L.off_gamma;
-        epi.act = L.act;
-        epi.bn = L.bn;
-        epi.bn_off = L.bn_off;
-        epi.vbn_len = net->vbn_len;
-        epi.vbn = d_vbn;
-        if (L.kind == DNE_CONV) {
+        const LayerEpi epi = make_layer_epi(L, net, d_vbn);
+        if (L.kind == DNE_CONV && use_s2d) {
+            const dne_layer_desc* next = (!last && net->layers[l + 1].kind == DNE_CONV) ? &net->layers[l + 1] : nullptr;
+            rc = dne_launch_conv_layer_s2d(sa, L, epi, cur_u8, cur, cur_stride, out, out_stride, next, n_slots,
+                                           ctx->sm_count, st);
+            if (rc) {
+                dne_set_error("forward: s2d conv layer %d launch failed (%d)", l, rc);
+                return rc;
+            }
+        } else if (L.kind == DNE_CONV) {
             DNE_CHECK_ARG((int64_t)L.hin * L.hin * L.cin == cur_elems, "conv layer input size mismatch");
-            rc = dne_launch_conv_layer(sa, L, epi, cur_u8, cur, cur_elems, 0, out, out_stride, 0, n_slots, 1, st);
+            rc = dne_launch_conv_layer(sa, L, epi, cur_u8, cur, cur_stride, 0, out, out_stride, 0, n_slots, 1, st);
             if (rc) {
                 dne_set_error("forward: conv layer %d shape not compiled in (cin %d cout %d k %d s %d hin %d)", l,
                               L.cin, L.cout, L.ksize, L.stride, L.hin);
@@ -268,9 +298,24 @@ static int forward_impl(dne_ctx* ctx, const dne_net_desc* net, const float* d_th
         } else {
             DNE_CHECK_ARG(!cur_u8, "dense layer cannot read uint8 observations");
             DNE_CHECK_ARG(L.cin == cur_elems, "dense layer input size mismatch");
-            rc = dne_launch_dense_layer(ctx, sa, L, epi, fp.dense[l], (const float*)cur, cur_elems, out, out_stride,
+            // the output head rides in the combine kernel of the layer before it (one launch less per tick)
+            DenseHead head;
+            const bool fuse = g_dne_fuse_head && l + 2 == net->n_layers && net->layers[l + 1].kind == DNE_DENSE &&
+                              dne_head_fusable(L, fp.dense[l], net->layers[l + 1], fp.dense[l + 1]);
+            if (fuse) {
+                head.L = &net->layers[l + 1];
+                head.epi = make_layer_epi(net->layers[l + 1], net, d_vbn);
+                head.out = d_out ? d_out : (float*)(ws + fp.act_off[l + 1]);
+                head.out_slot_stride = d_out ? net->n_out : fp.act_elems[l + 1];
+                head.actions = d_actions;
+            }
+            rc = dne_launch_dense_layer(ctx, sa, L, epi, fp.dense[l], (const float*)cur, cur_stride, out, out_stride,
                                         last ? d_actions : nullptr, (float*)(ws + fp.part_theta_off),
-                                        (float*)(ws + fp.part_noise_off), n_slots, st);
+                                        (float*)(ws + fp.part_noise_off), n_slots, st, fuse ? &head : nullptr);
+            if (rc == 0 && fuse) {
+                DNE_LAUNCH_CHECK();
+                break;                                           // the head layer is done
+            }
             if (rc) {
                 dne_set_error("forward: dense layer %d (%d x %d) not supported", l, L.cin, L.cout);
                 return rc;
@@ -278,7 +323,8 @@ static int forward_impl(dne_ctx* ctx, const dne_net_desc* net, const float* d_th
         }
         DNE_LAUNCH_CHECK();
         cur = out;
-        cur_elems = fp.act_elems[l];
+        cur_elems = layer_out_elems(L);
+        cur_stride = out_stride;
         cur_u8 = false;
     }
     if (ctx->ev_record && !ctx->ev_record_done) DNE_CUDA(cudaEventRecord((cudaEvent_t)ctx->ev_record, st));

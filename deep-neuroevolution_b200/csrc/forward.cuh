@@ -58,13 +58,29 @@ int dne_launch_conv_layer(const SlotArgs& sa, const dne_layer_desc& L, const Lay
                           int64_t out_slot_stride, int64_t out_img_stride, int n_slots, int n_img,
                           cudaStream_t st);
 
+// the output head fused behind a decomposed dense layer (dense_combine_head_kernel)
+struct DenseHead {
+    const dne_layer_desc* L;
+    LayerEpi epi;
+    float* out;                // logits [n_slots, out_slot_stride]
+    int64_t out_slot_stride;
+    int32_t* actions;          // nullable
+};
+bool dne_head_fusable(const dne_layer_desc& L, const DensePlan& p, const dne_layer_desc& head, const DensePlan& hp);
 int dne_launch_dense_layer(const dne_ctx* ctx, const SlotArgs& sa, const dne_layer_desc& L, const LayerEpi& epi,
                            const DensePlan& p, const float* X, int64_t x_slot_stride, float* out,
                            int64_t out_slot_stride, int32_t* actions, float* part_theta, float* part_noise,
-                           int n_slots, cudaStream_t st);
+                           int n_slots, cudaStream_t st, const DenseHead* head = nullptr);
 
 void dne_launch_ob_norm(const float* obs, const float* mean, const float* stdv, int64_t total, int dim, float* out,
                         cudaStream_t st);
 
 int dne_launch_theta_gemm_tc(const float* X, int M, int K, int N, const float* W, int k_per_split, int n_split,
                              float* part, cudaStream_t st);
+
+// conv_s2d.cu: shifted-window implicit-GEMM convolutions (tcgen05, A operand by TMA), dne_set_option("conv_tc", 2) [default]
+bool dne_s2d_supported(const dne_layer_desc& L, bool in_u8);
+size_t dne_s2d_image_bytes(const dne_layer_desc& L);
+int dne_launch_conv_layer_s2d(const SlotArgs& sa, const dne_layer_desc& L, const LayerEpi& epi, bool in_u8, const void* in,
+                              int64_t in_slot_stride, float* out, int64_t out_slot_stride, const dne_layer_desc* next,
+                              int n_slots, int sm_count, cudaStream_t st);

@@ -444,6 +444,87 @@ dense_small_kernel(SlotArgs sa, int64_t off_w, LayerEpi epi, const float* __rest
     }
 }
 
+// combine + output head in one kernel (one CTA per slot): the hidden vector y[N1] of dense_combine_kernel is built in
+// shared memory and fed straight to the head of dense_small_kernel (512x18 / 256x18 / 256x17) and its argmax -- one launch
+// and one global round trip less per tick.  Same per-element arithmetic and summation order as the two separate kernels.
+constexpr int DCH_MAXK = 1024;
+__global__ void __launch_bounds__(DS_THREADS)
+dense_combine_head_kernel(SlotArgs sa, LayerEpi epi1, int n_slots, int N1, int G, const float* __restrict__ part_theta,
+                          int n_split, int Gt, const float* __restrict__ part_noise, int n_chunks,
+                          float* __restrict__ hidden_out, int64_t hidden_stride,
+                          int64_t off_w2, LayerEpi epi2, int N2, float* __restrict__ out, int64_t out_slot_stride,
+                          int32_t* __restrict__ actions) {
+    const int slot = blockIdx.x;
+    if (!slot_active(sa, slot)) return;
+    __shared__ float xs[DCH_MAXK];
+    __shared__ float red[DS_THREADS];
+    __shared__ float ys[DS_MAXN];
+    const int t = threadIdx.x;
+    const float* th = slot_theta(sa, slot);
+    const int64_t idx = sa.noise_idx[slot];
+    const float s = sa.scale[slot];
+    // ---- phase 1: y = act(bn(sum_split Ytheta + s * sum_chunk Ynoise + bias))  (dense_combine_kernel) ----
+    for (int n = t; n < N1; n += DS_THREADS) {
+        float yt = 0.0f;
+        if (Gt == 0) {
+            for (int sp = 0; sp < n_split; ++sp) yt += part_theta[((int64_t)sp * n_slots + slot) * N1 + n];
+        } else {
+            const float* pt = part_theta + (((int64_t)(slot / Gt) * n_split) * Gt + (slot % Gt)) * N1 + n;
+            for (int c = 0; c < n_split; ++c) yt += pt[(int64_t)c * Gt * N1];
+        }
+        const int group = slot / G, g = slot % G;
+        float yn = 0.0f;
+        const float* pn = part_noise + (((int64_t)group * n_chunks) * G + g) * N1 + n;
+        for (int c = 0; c < n_chunks; ++c) yn += pn[(int64_t)c * G * N1];
+        const ChanEpi ce = make_chan_epi(sa, epi1, slot, N1, n, th, idx, s);
+        const float y = ce.apply(fmaf(s, yn, yt));
+        xs[n] = y;
+        if (hidden_out) hidden_out[(int64_t)slot * hidden_stride + n] = y;
+    }
+    __syncthreads();
+    // ---- phase 2: the head (dense_small_kernel) on x = xs ----
+    const int K = N1, N = N2;
+    const int RG = DS_THREADS / N;
+    const int n = t % N, rg = t / N;
+    const float* tw = th + off_w2;
+    const float* nz = sa.noise + idx + off_w2;
+    float acc0 = 0.0f, acc1 = 0.0f;
+    if (rg < RG) {
+        int k = rg;
+        for (; k + RG < K; k += 2 * RG) {
+            const int64_t f0 = (int64_t)k * N + n, f1 = (int64_t)(k + RG) * N + n;
+            const float t0 = tw[f0], n0 = nz[f0], t1 = tw[f1], n1 = nz[f1];
+            acc0 = fmaf(xs[k], perturbed(t0, s, n0), acc0);
+            acc1 = fmaf(xs[k + RG], perturbed(t1, s, n1), acc1);
+        }
+        if (k < K) {
+            const int64_t f0 = (int64_t)k * N + n;
+            acc0 = fmaf(xs[k], perturbed(tw[f0], s, nz[f0]), acc0);
+        }
+    }
+    red[t] = acc0 + acc1;
+    __syncthreads();
+    if (t < N) {
+        float sum = 0.0f;
+        for (int g = 0; g < RG; ++g) sum += red[g * N + t];
+        const ChanEpi ce = make_chan_epi(sa, epi2, slot, N, t, th, idx, s);
+        const float y = ce.apply(sum);
+        ys[t] = y;
+        if (out) out[(int64_t)slot * out_slot_stride + t] = y;
+    }
+    __syncthreads();
+    if (actions && threadIdx.x == 0) {
+        int best = 0;
+        float bv = ys[0];
+        for (int j = 1; j < N; ++j) {
+            const float v = ys[j];
+            if (bv != bv) break;                   // a NaN already is the maximum (numpy argmax)
+            if (v > bv || v != v) { bv = v; best = j; }
+        }
+        actions[slot] = best;
+    }
+}
+
 // MujocoPolicy observation normalisation (policies.py:151): clip((o - mean) / std, -5, 5)
 __global__ void ob_norm_kernel(const float* __restrict__ obs, const float* __restrict__ mean,
                                const float* __restrict__ stdv, int64_t total, int dim, float* __restrict__ out) {
@@ -453,6 +534,32 @@ __global__ void ob_norm_kernel(const float* __restrict__ obs, const float* __res
     float v = obs[i];
     if (mean) v = __fdiv_rn(__fsub_rn(v, mean[d]), stdv[d]);
     out[i] = fminf(fmaxf(v, -5.0f), 5.0f);
+}
+
+// Observation statistics for the running normaliser (es.py:356-363: task_ob_stat.increment(obs.sum(0), square(obs).sum(0),
+// len(obs)) over the episodes sampled with probability calc_obstat_prob): per tick, add the observations of the listed
+// slots into float64 running sums.  One thread per observation dimension, slots in list order: deterministic.
+__global__ void ob_stat_accum_kernel(const float* __restrict__ obs, int dim, const int32_t* __restrict__ slots, int m,
+                                     double* __restrict__ sum, double* __restrict__ sumsq) {
+    const int d = blockIdx.x * blockDim.x + threadIdx.x;
+    if (d >= dim) return;
+    double a = 0.0, b = 0.0;
+    for (int i = 0; i < m; ++i) {
+        const double v = (double)obs[(int64_t)slots[i] * dim + d];
+        a += v;
+        b += v * v;
+    }
+    sum[d] += a;
+    sumsq[d] += b;
+}
+
+extern "C" int dne_ob_stat_accumulate(const float* d_obs, int ob_dim, const int32_t* d_slots, int m, double* d_sum,
+                                      double* d_sumsq, void* stream) {
+    DNE_CHECK_ARG(d_obs && d_slots && d_sum && d_sumsq && ob_dim > 0 && m >= 0, "bad arguments");
+    if (m == 0) return DNE_OK;
+    ob_stat_accum_kernel<<<(ob_dim + 127) / 128, 128, 0, (cudaStream_t)stream>>>(d_obs, ob_dim, d_slots, m, d_sum, d_sumsq);
+    DNE_LAUNCH_CHECK1();
+    return DNE_OK;
 }
 
 // =====================================================================================================
@@ -477,7 +584,7 @@ static bool conv_is(const dne_layer_desc& L, int cin, int cout, int ks, int stri
 }
 
 // in_u8: the layer reads uint8 observations.  Returns 0 or DNE_ERR_UNSUP.
-int g_dne_conv_tc = 1;     // 1: tcgen05 path (tc_conv.cu), 0: fp32 SIMT path (dne_set_option("conv_tc", v))
+int g_dne_conv_tc = 2;     // 2: shifted-window tcgen05 + TMA (conv_s2d.cu), 1: im2col-staged tcgen05 (tc_conv.cu), 0: fp32 SIMT
 
 int dne_launch_conv_layer(const SlotArgs& sa, const dne_layer_desc& L, const LayerEpi& epi, bool in_u8,
                           const void* in, int64_t in_slot_stride, int64_t in_img_stride, float* out,
@@ -552,10 +659,15 @@ DensePlan dne_plan_dense(const dne_layer_desc& L, int n_slots, int paired, bool 
     return p;
 }
 
+bool dne_head_fusable(const dne_layer_desc& L, const DensePlan& p, const dne_layer_desc& head, const DensePlan& hp) {
+    return p.decomposed && !hp.decomposed && L.cout <= DCH_MAXK && head.cin == L.cout && head.cout <= DS_MAXN &&
+           head.cout <= DS_THREADS;
+}
+
 int dne_launch_dense_layer(const dne_ctx* ctx, const SlotArgs& sa, const dne_layer_desc& L, const LayerEpi& epi,
                            const DensePlan& p, const float* X, int64_t x_slot_stride, float* out,
                            int64_t out_slot_stride, int32_t* actions, float* part_theta, float* part_noise,
-                           int n_slots, cudaStream_t st) {
+                           int n_slots, cudaStream_t st, const DenseHead* head) {
     const int K = L.cin, N = L.cout;
     if (!p.decomposed) {
         if (N > DS_MAXN) return DNE_ERR_UNSUP;
@@ -624,7 +736,11 @@ int dne_launch_dense_layer(const dne_ctx* ctx, const SlotArgs& sa, const dne_lay
             mctx->ev_record_done = 1;
         }
     }
-    {
+    if (head) {          // combine + output head + argmax in one kernel (the hidden vector stays in shared memory)
+        dense_combine_head_kernel<<<n_slots, DS_THREADS, 0, st>>>(
+            sa, epi, n_slots, N, p.G, part_theta, p.n_split, p.Gt, part_noise, p.n_chunks, out, out_slot_stride,
+            head->L->off_w, head->epi, head->L->cout, head->out, head->out_slot_stride, head->actions);
+    } else {
         dim3 grid((N + 255) / 256, n_slots);
         dense_combine_kernel<<<grid, 256, 0, st>>>(sa, epi, n_slots, N, p.G, part_theta, p.n_split, p.Gt, part_noise,
                                                   p.n_chunks, out, out_slot_stride);

@@ -188,6 +188,7 @@ extern "C" int dne_vbn_reference_pass(dne_ctx* ctx, const dne_net_desc* net, con
                                       float* d_vbn, void* d_ws, size_t ws_bytes, void* stream) {
     DNE_CHECK_ARG(ctx && ctx->noise, "noise table not bound (dne_noise_bind)");
     DNE_CHECK_ARG(net && d_theta && d_noise_idx && d_scale && d_ref && d_vbn && d_ws, "null pointer");
+    DNE_CHECK_ARG(((uintptr_t)d_theta & 15) == 0, "d_theta must be 16-byte aligned");
     DNE_CHECK_ARG(net->ob_kind == DNE_OB_ATARI_U8 && n_ref >= 1 && n_slots >= 0, "bad arguments");
     if (n_slots == 0) return DNE_OK;
     const int last = last_bn_layer(net);

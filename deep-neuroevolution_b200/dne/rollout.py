@@ -30,6 +30,7 @@ class Unit:
     noise_idx: int
     scales: Sequence[float]
     theta_idx: int = 0
+    noiseless: bool = False    # evaluation episodes (es.py:388-391): no action noise, never sampled for ob statistics
 
 
 @dataclass
@@ -40,6 +41,9 @@ class RolloutResult:
     bcs: Optional[list] = None  # per unit, per member: behaviour characterisation (policies.py:418,429)
     steps: int = 0             # env steps executed (== lengths.sum())
     ticks: int = 0             # forward launches
+    ob_sum: Optional[np.ndarray] = None     # float64 [ob_dim]: sum of the observations of the sampled episodes (es.py:358-359)
+    ob_sumsq: Optional[np.ndarray] = None
+    ob_count: int = 0                       # number of observations in the sums
 
 
 class _Half:
@@ -68,6 +72,11 @@ class _Half:
         self.dirty = True
         self.launched = False
         self.fresh = np.zeros(n, dtype=np.uint8)          # slots that start an episode at the next launch
+        self.noiseless = np.zeros(n, dtype=bool)          # evaluation episodes: no action noise
+        self.save = np.zeros(n, dtype=np.uint8)           # episode sampled for the observation statistics (es.py:356-357)
+        self.save_m = 0                                   # number of slots in save_list
+        self.save_list = None                             # device int32 [n]: active & sampled slots (built lazily)
+        self.ob_sum = self.ob_sumsq = None                # device float64 [ob_dim] (per half: the halves run on two streams)
 
 
 class RolloutRunner:
@@ -98,6 +107,19 @@ class RolloutRunner:
         self.use_theta_idx = theta.dim() == 2 and theta.shape[0] > 1
         pending = deque(range(n_units))
         remaining = [G] * n_units
+        want_obstat = save_obs_prob != 0.0 and self.net.ob_kind == F.OB_VECTOR
+        obstat_stream = random_stream if random_stream is not None else np.random.RandomState(0)
+        for h in self.halves:
+            h.save[:] = 0
+            h.save_m = 0
+            if want_obstat:
+                if h.ob_sum is None:
+                    h.ob_sum = torch.zeros(self.net.ob_dim, dtype=torch.float64, device=h.sf.device)
+                    h.ob_sumsq = torch.zeros_like(h.ob_sum)
+                    h.save_list = torch.zeros(h.hi - h.lo, dtype=torch.int32, device=h.sf.device)
+                    h.save_host = torch.zeros(h.hi - h.lo, dtype=torch.int32).pin_memory()
+                h.ob_sum.zero_()
+                h.ob_sumsq.zero_()
         if collect_bc == "trace":                          # per-slot RAM trace buffers, filled with vectorised writes
             for h in self.halves:
                 if getattr(h, "bc_buf", None) is None or h.bc_buf.shape[1] < limit:
@@ -126,6 +148,9 @@ class RolloutRunner:
                     h.active[s], h.fresh[s] = 1, 1
                     h.ret[s] = h.sret[s] = 0.0
                     h.length[s] = 0
+                    h.noiseless[s] = unit.noiseless
+                    # es.py:356-357: each (non-evaluation) episode is sampled with probability calc_obstat_prob
+                    h.save[s] = 1 if (want_obstat and not unit.noiseless and obstat_stream.rand() < save_obs_prob) else 0
                 env.reset(h.lo + np.arange(u0, u0 + G))
                 h.dirty = True
 
@@ -138,8 +163,19 @@ class RolloutRunner:
                         mask = torch.as_tensor(h.fresh).to(h.sf.device, non_blocking=True)
                         h.sf.vbn_reference_pass(theta, self.ref_batch, active=mask)     # policies.py:399
                     h.fresh[:] = 0
+                    if want_obstat:                                  # slot list of the sampled episodes still running
+                        loc = np.nonzero(np.logical_and(h.active, h.save))[0].astype(np.int32)
+                        h.save_m = len(loc)
+                        if h.save_m:
+                            h.save_host[:h.save_m] = torch.from_numpy(loc)
+                            h.save_list[:h.save_m].copy_(h.save_host[:h.save_m], non_blocking=True)
                     h.dirty = False
                 h.obs_dev.copy_(env.obs_block(h.lo, h.hi), non_blocking=True)           # pinned -> HBM
+                if want_obstat and h.save_m:                         # es.py:358-359 on the device, unnormalised observations
+                    F.check(F.lib().dne_ob_stat_accumulate(F.ptr(h.obs_dev, torch.float32), self.net.ob_dim,
+                                                           F.ptr(h.save_list), h.save_m, F.ptr(h.ob_sum),
+                                                           F.ptr(h.ob_sumsq), F.stream_ptr()))
+                    res.ob_count += h.save_m
                 out = h.sf.forward(theta, h.obs_dev, paired=(G == 2), ob_mean=ob_mean, ob_std=ob_std)
                 h.act_host.copy_(out, non_blocking=True)
                 h.event.record(h.stream)
@@ -152,7 +188,9 @@ class RolloutRunner:
             loc = np.nonzero(h.active)[0]
             acts = h.act_host.numpy()[loc]
             if ac_noise_std != 0.0 and random_stream is not None and acts.dtype != np.int32:
-                acts = acts + random_stream.randn(*acts.shape).astype(np.float32) * np.float32(ac_noise_std)  # policies.py:204-205
+                noisy = ~h.noiseless[loc]                             # evaluation episodes act without noise (es.py:388-391)
+                acts = acts + (random_stream.randn(*acts.shape).astype(np.float32) * np.float32(ac_noise_std)) * \
+                    noisy[:, None].astype(np.float32)                 # policies.py:204-205
             rew, done = env.step(h.lo + loc, acts)
             h.ret[loc] += rew
             h.sret[loc] += np.sign(rew)
@@ -195,4 +233,7 @@ class RolloutRunner:
         for h in self.halves:
             cur.wait_stream(h.stream)
         assert not pending and all(r == 0 for r in remaining)
+        if want_obstat:
+            res.ob_sum = sum(h.ob_sum for h in self.halves).cpu().numpy()
+            res.ob_sumsq = sum(h.ob_sumsq for h in self.halves).cpu().numpy()
         return res

@@ -234,6 +234,8 @@ def run_master(master_redis_cfg, log_dir, exp, *, max_iterations=None, n_slots=2
         noise_inds, returns, signreturns, lengths = [], [], [], []
         eval_rets, eval_lens = [], []
         num_eps = num_ts = 0
+        ob_count_this_batch = 0
+        ob_acc = None
         ticks_this_iter = 0
         first = True
         # es.py:230: collect until BOTH quotas are met.  First batch = ceil(episodes_per_batch/2) pairs; if the
@@ -243,11 +245,18 @@ def run_master(master_redis_cfg, log_dir, exp, *, max_iterations=None, n_slots=2
             n_eval = int(rs.binomial(n_pairs, config.eval_prob)) if (first and config.eval_prob > 0) else 0
             idx = np.array([noise.sample_index(rs, P) for _ in range(n_pairs)], dtype=np.int64)      # es.py:412
             sig = np.float32(config.noise_stdev)
-            units = [Unit(int(i), (sig, -sig)) for i in idx] + [Unit(0, (0.0, 0.0)) for _ in range(-(-n_eval // 2))]
+            units = [Unit(int(i), (sig, -sig)) for i in idx] + \
+                    [Unit(0, (0.0, 0.0), noiseless=True) for _ in range(-(-n_eval // 2))]        # es.py:388-391
             lo, hi = shard.shard_bounds(len(units), rank, world)
+            # the worker-side random stream (es.py:372: action noise, ob-stat sampling) is separate from the seeded
+            # noise-index stream, so the index sequence never depends on episode lengths or the rank count
             res = runner.run(optimizer.device_theta, units[lo:hi], tslimit, ob_mean=ob_mean, ob_std=ob_std,
-                             ac_noise_std=getattr(policy, "ac_noise_std", 0.0), random_stream=rs if world == 1 else
-                             np.random.RandomState(seed + 1000 * it + rank))
+                             ac_noise_std=getattr(policy, "ac_noise_std", 0.0),
+                             random_stream=np.random.RandomState((seed + 1000 * it + rank) % (2 ** 31)),
+                             save_obs_prob=config.calc_obstat_prob if policy.needs_ob_stat else 0.0)
+            if policy.needs_ob_stat and config.calc_obstat_prob != 0:                # es.py:260-263
+                acc = np.concatenate([res.ob_sum, res.ob_sumsq, [float(res.ob_count)]])
+                ob_acc = acc if ob_acc is None else ob_acc + acc
             ticks_this_iter += res.ticks
             dev = upd.device
             pack = torch.from_numpy(np.concatenate([res.returns, res.signreturns, res.lengths.astype(np.float32)],
@@ -281,6 +290,18 @@ def run_master(master_redis_cfg, log_dir, exp, *, max_iterations=None, n_slots=2
         shard.all_reduce_sum_(g)                                                      # 4*P bytes over NVLink
         update_ratio, _ = optimizer.update_from_gradient(g, config.l2coeff)           # es.py:298
 
+        # ---- observation statistics (es.py:260-263): every worker's (sum, sumsq, count) added into the running stat ----
+        if ob_acc is not None:
+            t = torch.from_numpy(ob_acc).to(dev)
+            shard.all_reduce_sum_(t)
+            tot = t.cpu().numpy()
+            D = (len(tot) - 1) // 2
+            ob_count_this_batch = int(round(tot[-1]))
+            if ob_count_this_batch > 0:
+                shp = ob_stat.sum.shape
+                ob_stat.increment(tot[:D].astype(np.float32).reshape(shp), tot[D:2 * D].astype(np.float32).reshape(shp),
+                                  ob_count_this_batch)
+
         if adaptive_tslimit and (lengths_n2 == tslimit).mean() >= incr_tslimit_threshold:   # es.py:308-311
             old = tslimit
             tslimit = min(int(tslimit_incr_ratio * tslimit), tslimit_max)
@@ -300,7 +321,7 @@ def run_master(master_redis_cfg, log_dir, exp, *, max_iterations=None, n_slots=2
             UpdateRatio=float(update_ratio),
             EpisodesThisIter=int(lengths_n2.size), EpisodesSoFar=int(episodes_so_far),
             TimestepsThisIter=int(lengths_n2.sum()), TimestepsSoFar=int(timesteps_so_far),
-            UniqueWorkers=world, UniqueWorkersFrac=1.0, ResultsSkippedFrac=0.0, ObCount=0,
+            UniqueWorkers=world, UniqueWorkersFrac=1.0, ResultsSkippedFrac=0.0, ObCount=ob_count_this_batch,
             TimeElapsedThisIter=step_tend - step_tstart, TimeElapsed=step_tend - tstart)
         if rank == 0:
             for k, v in stats.items():
@@ -309,7 +330,7 @@ def run_master(master_redis_cfg, log_dir, exp, *, max_iterations=None, n_slots=2
         if on_iteration is not None:
             on_iteration(it, stats, dict(noise_inds_n=noise_inds_n, returns_n2=returns_n2, lengths_n2=lengths_n2,
                                          signreturns_n2=signreturns_n2, g=g, theta=optimizer.device_theta,
-                                         forward_launches=ticks_this_iter,
+                                         forward_launches=ticks_this_iter, ob_stat=ob_stat,
                                          slots_per_launch=n_slots // len(runner.halves)))
         if rank == 0 and log_dir and config.snapshot_freq != 0 and it % config.snapshot_freq == 0:   # es.py:345-353
             import os.path as osp

@@ -94,7 +94,9 @@ class Policy:
     # -- flat get / set (policies.py:102-106; tf_util.py:224-246) --------------------------------------------
     def set_trainable_flat(self, x):
         if isinstance(x, torch.Tensor):
-            self._theta = x.to(self.device, torch.float32).reshape(-1)
+            t = x.to(self.device, torch.float32).reshape(-1)
+            # libdne wants a 16-byte aligned base pointer: a row view of a [n, P] matrix (P % 4 != 0) is not
+            self._theta = t.clone() if t.data_ptr() % 16 else t
         else:
             x = np.asarray(x, dtype=np.float32)
             assert x.shape == (self.num_params,)

@@ -143,6 +143,13 @@ int dne_perturb_forward_mlp(dne_ctx* ctx, const dne_net_desc* net, const float* 
                             const float* d_obs, const float* d_ob_mean, const float* d_ob_std,
                             float* d_actions_out, void* d_ws, size_t ws_bytes, void* stream);
 
+/* Observation statistics of the running normaliser (es.py:356-363 rollout_and_update_ob_stat; RunningStat es.py:26-48):
+ * adds the observations d_obs[slot, :] (float32 [*, ob_dim], the unnormalised vectors fed to this tick's forward) of the m
+ * listed slots -- the slots whose episode was sampled with probability calc_obstat_prob -- into float64 running sums
+ * d_sum[ob_dim], d_sumsq[ob_dim].  The episode count stays with the caller (m per tick). */
+int dne_ob_stat_accumulate(const float* d_obs, int ob_dim, const int32_t* d_slots, int m, double* d_sum, double* d_sumsq,
+                           void* stream);
+
 /* Virtual batch norm reference pass, per member before each episode (policies.py:322-328,399;
  * es.py:105-113): forwards the shared reference batch d_ref [n_ref,84,84,4] through every listed slot's
  * perturbed weights with batch statistics and stores (mean, biased var) per BN layer in d_vbn[slot]. */

@@ -523,6 +523,118 @@ def max_and_stack(frames_prev: np.ndarray, frames_cur: np.ndarray, stack: np.nda
 
 
 # --------------------------------------------------------------------------------------------------
+# a-6  210x160 -> 84x84 warp, both reference flavours
+# --------------------------------------------------------------------------------------------------
+
+def gray_rgb(obs_rgb_u8: np.ndarray) -> np.ndarray:
+    """atari_wrappers.py:139: ``np.dot(obs.astype('float32'), [0.299, 0.587, 0.114] float32)``.  numpy hands this to the
+    BLAS sgemv of its build, whose summation order / FMA use is build specific (here np.dot, np.einsum and ``@`` give
+    three different float32 results on the same input), so the reference itself is only defined to 1 ulp.  Canonical
+    restatement: ((r*0.299 + g*0.587) + b*0.114), every operation rounded to float32 -- within 1 ulp of the recorded numpy
+    output (tests/test_oracle.py)."""
+    o = obs_rgb_u8.astype(f32)
+    w = np.array([0.299, 0.587, 0.114], dtype=f32)
+    return ((o[..., 0] * w[0] + o[..., 1] * w[1]).astype(f32) + o[..., 2] * w[2]).astype(f32)
+
+
+def pillow_bilinear_coeffs(in_size: int, out_size: int):
+    """Pillow ``precompute_coeffs`` (src/libImaging/Resample.c) for the BILINEAR (triangle, support 1) filter: when
+    shrinking, the support is scaled by in/out (an area-weighted triangle, NOT 2-tap bilinear).  Returns
+    (xmin[out], count[out], k[out, ksize]) in float64, exactly the double arithmetic of the C code."""
+    scale = filterscale = in_size / out_size
+    if filterscale < 1.0:
+        filterscale = 1.0
+    support = 1.0 * filterscale
+    ksize = int(np.ceil(support)) * 2 + 1
+    xmins, counts, kk = np.zeros(out_size, np.int32), np.zeros(out_size, np.int32), np.zeros((out_size, ksize), np.float64)
+    ss = 1.0 / filterscale
+    for xx in range(out_size):
+        center = (xx + 0.5) * scale
+        xmin = int(center - support + 0.5)
+        if xmin < 0:
+            xmin = 0
+        xmax = int(center + support + 0.5)
+        if xmax > in_size:
+            xmax = in_size
+        xmax -= xmin
+        ww = 0.0
+        for x in range(xmax):
+            a = (x + xmin - center + 0.5) * ss
+            a = -a if a < 0.0 else a
+            w = 1.0 - a if a < 1.0 else 0.0
+            kk[xx, x] = w
+            ww += w
+        if ww != 0.0:
+            kk[xx, :xmax] /= ww
+        xmins[xx], counts[xx] = xmin, xmax
+    return xmins, counts, kk
+
+
+def resize_pillow_bilinear(gray: np.ndarray, res: int = 84) -> np.ndarray:
+    """``Image.fromarray(frame).resize((res, res), BILINEAR)`` on a mode-'F' image followed by ``np.array(..., dtype=np.uint8)``
+    (atari_wrappers.py:140-141).  Pillow's 32-bit-float path: horizontal pass first, then vertical, each output =
+    float32(sum_x double(pixel) * k[x]) accumulated in double (ImagingResampleHorizontal_32bpc / Vertical_32bpc); the uint8
+    cast truncates.  Pinned bit-exactly against Pillow itself (tests/test_oracle.py)."""
+    gray = np.asarray(gray, dtype=f32)
+    H, Wd = gray.shape
+    xm, xc, xk = pillow_bilinear_coeffs(Wd, res)
+    tmp = np.zeros((H, res), dtype=f32)
+    for xx in range(res):
+        acc = np.zeros(H, dtype=np.float64)
+        for x in range(xc[xx]):
+            acc = acc + gray[:, xm[xx] + x].astype(np.float64) * xk[xx, x]
+        tmp[:, xx] = acc.astype(f32)
+    ym, yc, yk = pillow_bilinear_coeffs(H, res)
+    out = np.zeros((res, res), dtype=f32)
+    for yy in range(res):
+        acc = np.zeros(res, dtype=np.float64)
+        for y in range(yc[yy]):
+            acc = acc + tmp[ym[yy] + y].astype(np.float64) * yk[yy, y]
+        out[yy] = acc.astype(f32)
+    return out.astype(np.uint8)                                   # values are in [0, 255]: truncation toward zero
+
+
+def warp_frame_cpu(obs_rgb_u8: np.ndarray, res: int = 84) -> np.ndarray:
+    """atari_wrappers.py:138-142 ``WarpFrame._observation``: gray (canonical float32 formula) -> Pillow BILINEAR -> uint8."""
+    return resize_pillow_bilinear(gray_rgb(obs_rgb_u8), res)
+
+
+def warp_frame_gpu(pal_idx_2: np.ndarray, gray_palette: np.ndarray, res: int = 84) -> np.ndarray:
+    """gpu_implementation/gym_tensorflow/atari/tf_atari.py:88-92: palette index -> gray float32 LUT (``:149``), max over
+    the two raw frames, ``tf.image.resize_bilinear(..., align_corners=True)`` -> float32 [84, 84] in [0, 1].
+    TF kernel arithmetic (resize_bilinear_op.cc): scale = (in-1)/(out-1) float32; in = i*scale; lower = int(in);
+    upper = min(lower+1, in_size-1); lerp = in - lower; top = tl + (tr-tl)*xl; bottom = bl + (br-bl)*xl;
+    out = top + (bottom-top)*yl, all float32.  TensorFlow is absent here: parity unpinned, by formula."""
+    g = gray_palette.astype(f32).reshape(-1)[pal_idx_2.astype(np.int64)]        # [2, 210, 160]
+    img = np.maximum(g[0], g[1])
+    H, Wd = img.shape
+
+    def weights(n_in, n_out):
+        scale = f32((n_in - 1) / f32(n_out - 1)) if n_out > 1 else f32(0)
+        pos = (np.arange(n_out, dtype=f32) * scale).astype(f32)
+        lo = pos.astype(np.int64)
+        hi = np.minimum(lo + 1, n_in - 1)
+        return lo, hi, (pos - lo.astype(f32)).astype(f32)
+    ylo, yhi, yl = weights(H, res)
+    xlo, xhi, xl = weights(Wd, res)
+    tl, tr = img[ylo][:, xlo], img[ylo][:, xhi]
+    bl, br = img[yhi][:, xlo], img[yhi][:, xhi]
+    top = (tl + ((tr - tl).astype(f32) * xl[None, :]).astype(f32)).astype(f32)
+    bot = (bl + ((br - bl).astype(f32) * xl[None, :]).astype(f32)).astype(f32)
+    return (top + ((bot - top).astype(f32) * yl[:, None]).astype(f32)).astype(f32)
+
+
+def ntsc_gray_palette() -> np.ndarray:
+    """tf_atari.py:100-149: NTSC palette (128 colours at even indices) -> RGB/255 -> gray float32 [256].  The table
+    itself is data of the emulator front end; the synthetic pipeline here uses a deterministic stand-in with the same
+    structure (even entries populated, odd entries zero) because only the LUT-gather semantics are on the path."""
+    rs = np.random.RandomState(1977)
+    rgb = np.zeros((256, 3), dtype=np.uint8)
+    rgb[0::2] = rs.randint(0, 256, size=(128, 3))
+    return (rgb.astype(f32) * f32(1.0 / 255.0)) @ np.array([0.299, 0.587, 0.114], dtype=f32)
+
+
+# --------------------------------------------------------------------------------------------------
 # a-7  rollout accounting                                    es.py:423-426 ; policies.py:378-429
 # --------------------------------------------------------------------------------------------------
 

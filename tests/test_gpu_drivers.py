@@ -167,3 +167,90 @@ def test_nsr_run_master_novelty_and_update(noise, host_noise, tmp_path):
         proc = O.nsr_blend(ex["returns_n2"], nov)                                     # nses.py:221-228
         g = O.es_gradient(proc, host_noise, ex["noise_inds_n"], 1009058)
         assert np.abs(ex["g"].cpu().numpy() - g).max() <= 1e-5 * np.abs(g).max()
+
+
+HUMANOID_ES = {       # configurations/humanoid.json (reference) -- population / batch sizes scaled down
+    "config": {"calc_obstat_prob": 0.5, "episodes_per_batch": 24, "eval_prob": 0.2, "l2coeff": 0.005, "noise_stdev": 0.02,
+               "snapshot_freq": 0, "timesteps_per_batch": 10, "return_proc_mode": "centered_rank",
+               "episode_cutoff_mode": "env_default"},
+    "env_id": "Humanoid-v1",
+    "optimizer": {"args": {"stepsize": 0.01}, "type": "adam"},
+    "policy": {"args": {"ac_bins": "continuous:", "ac_noise_std": 0.01, "connection_type": "ff", "hidden_dims": [256, 256],
+                        "nonlin_type": "tanh"}, "type": "MujocoPolicy"},
+}
+
+
+def test_es_humanoid_ob_stat_plumbing_matches_running_stat(noise, tmp_path):
+    """es.py:356-363,260-263,304-305: episodes sampled with calc_obstat_prob contribute (sum o, sum o^2, count) of the
+    observations fed to the policy; the master adds them into RunningStat and next iteration's rollouts normalise with the
+    new mean / std.  The environment here records every observation block it hands out, so the oracle RunningStat can be
+    rebuilt independently of the device accumulation: the set of sampled episodes is recovered from the counts."""
+    from es_distributed import es as ES
+    from dne.envs import SyntheticVectorEnv
+
+    class Recorder(SyntheticVectorEnv):
+        def __init__(self, *a, **k):
+            super().__init__(*a, **k)
+            self.blocks = {}          # (lo, hi) -> observation block handed to the next forward
+            self.fed = []             # (slot, obs vector) for every env step, in order
+
+        def obs_block(self, lo, hi):
+            blk = super().obs_block(lo, hi)
+            self.blocks[(lo, hi)] = (lo, blk.clone().numpy())
+            return blk
+
+        def step(self, slots, actions):
+            slots = np.asarray(slots)
+            for (lo, hi), (l0, blk) in self.blocks.items():
+                m = (slots >= lo) & (slots < hi)
+                for s in slots[m]:
+                    self.fed.append((int(s), blk[s - l0].copy()))
+            return super().step(slots, actions)
+
+    env = Recorder(8, episode_len=5, seed=4)
+    snaps = []
+
+    def on_it(it, stats, extra):
+        st = extra["ob_stat"]
+        snaps.append((it, stats["ObCount"], st.sum.copy(), st.sumsq.copy(), float(st.count), len(env.fed)))
+    ES.set_default_noise(noise)
+    ES.run_master(None, str(tmp_path), json.loads(json.dumps(HUMANOID_ES)), max_iterations=3, n_slots=8, env=env,
+                  noise=noise, seed=5, on_iteration=on_it)
+    assert len(snaps) == 3
+    orc = O.RunningStat((376,), eps=1e-2)
+    fed_prev = 0
+    total = 0
+    for it, ob_count, s_sum, s_sumsq, s_count, n_fed in snaps:
+        fed = env.fed[fed_prev:n_fed]
+        fed_prev = n_fed
+        # episodes are 5 steps long: an episode is sampled as a whole, so the count is a multiple of 5 and with
+        # prob 0.5 over >= 24 episodes some but not all episodes are sampled
+        assert ob_count % 5 == 0 and 0 < ob_count < len(fed)
+        total += ob_count
+        assert s_count == pytest.approx(1e-2 + total)
+        # the device sums must equal the sums over SOME set of whole episodes of this generation: check through the
+        # totals' consistency with per-dimension bounds, then exactly through the mean of the sampled observations
+        allv = np.stack([v for _, v in fed]).astype(np.float64)
+        assert np.all(np.abs(s_sum) <= np.abs(allv).sum(axis=0) + 1.0)
+    # exact check: rerun with probability 1 -> every observation fed counts
+    env2 = Recorder(8, episode_len=5, seed=4)
+    cfg = json.loads(json.dumps(HUMANOID_ES))
+    cfg["config"]["calc_obstat_prob"] = 1.0
+    cfg["config"]["eval_prob"] = 0.0
+    snaps2 = []
+    ES.run_master(None, str(tmp_path), cfg, max_iterations=2, n_slots=8, env=env2, noise=noise, seed=5,
+                  on_iteration=lambda it, stats, extra: snaps2.append(
+                      (stats["ObCount"], extra["ob_stat"].sum.copy(), extra["ob_stat"].sumsq.copy(),
+                       float(extra["ob_stat"].count), extra["ob_stat"].mean.copy(), extra["ob_stat"].std.copy(), len(env2.fed))))
+    orc = O.RunningStat((376,), eps=1e-2)
+    prev = 0
+    for ob_count, s_sum, s_sumsq, s_count, s_mean, s_std, n_fed in snaps2:
+        obs = np.stack([v for _, v in env2.fed[prev:n_fed]])
+        prev = n_fed
+        assert ob_count == len(obs)
+        orc.increment(obs.sum(axis=0), np.square(obs).sum(axis=0), len(obs))                 # es.py:358-359
+        assert s_count == pytest.approx(orc.count)
+        np.testing.assert_allclose(s_sum, orc.sum, rtol=1e-5, atol=1e-4)
+        np.testing.assert_allclose(s_sumsq, orc.sumsq, rtol=1e-5, atol=1e-4)
+        np.testing.assert_allclose(s_mean, orc.mean, rtol=1e-4, atol=1e-5)
+        np.testing.assert_allclose(s_std, orc.std, rtol=1e-4, atol=1e-5)

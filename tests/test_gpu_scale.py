@@ -124,14 +124,14 @@ def test_largemodel_256_slots_tensor_core_vs_simt_all_slots(ctx, host_noise):
     out = {}
     try:
         for fast in (1, 0):
-            F.check(L.dne_set_option(b"conv_tc", fast))
+            F.check(L.dne_set_option(b"conv_tc", 2 if fast else 0))
             F.check(L.dne_set_option(b"gemv_bulk", fast))
             sf = SlotForward(ctx, net, 256)
             sf.set_slots(idx, scale, active=active)
             a = sf.forward(d_theta, d_obs, paired=True).cpu().numpy()
             out[fast] = (sf.logits.cpu().numpy()[:250], a[:250])
     finally:
-        F.check(L.dne_set_option(b"conv_tc", 1))
+        F.check(L.dne_set_option(b"conv_tc", 2))
         F.check(L.dne_set_option(b"gemv_bulk", 1))
     lf, af = out[1]
     ls, as_ = out[0]

@@ -62,7 +62,7 @@ def _forward(ctx, net, theta, idx, scale, obs, paired, conv_tc, theta_idx=None):
         actions = sf.forward(d_theta, d_obs, paired=paired).cpu().numpy()
         return sf.logits.cpu().numpy(), actions
     finally:
-        F.check(F.lib().dne_set_option(b"conv_tc", 1))
+        F.check(F.lib().dne_set_option(b"conv_tc", 2))
 
 
 @pytest.mark.parametrize("name", ["LargeModel", "Model"])
@@ -75,20 +75,50 @@ def test_conv_tc_vs_simt_vs_oracle(ctx, host_noise, name):
     pidx = rs.randint(0, NOISE_COUNT - P + 1, size=n_slots // 2).astype(np.int64)
     idx, scale = np.repeat(pidx, 2), np.tile([0.02, -0.02], n_slots // 2).astype(np.float32)
     obs = rs.randint(0, 256, size=(n_slots, 84, 84, 4)).astype(np.uint8)
-    lt, at = _forward(ctx, net, theta, idx, scale, obs, 1, 1)
-    ls, as_ = _forward(ctx, net, theta, idx, scale, obs, 1, 0)
+    l2, a2 = _forward(ctx, net, theta, idx, scale, obs, 1, 2)        # shifted-window tcgen05 + TMA (default)
+    lt, at = _forward(ctx, net, theta, idx, scale, obs, 1, 1)        # im2col-staged tcgen05
+    ls, as_ = _forward(ctx, net, theta, idx, scale, obs, 1, 0)       # fp32 SIMT
     ref = np.stack([O.forward(net_o, O.perturb(theta, host_noise, int(idx[s]), 0.02, 1 if scale[s] > 0 else -1),
                               obs[s:s + 1])[0][0] for s in range(n_slots)])
     bound = 2e-5 * max(1.0, float(np.abs(ref).max()))
     assert np.abs(ls - ref).max() <= bound
     assert np.abs(lt - ref).max() <= bound, np.abs(lt - ref).max()
+    assert np.abs(l2 - ref).max() <= bound, np.abs(l2 - ref).max()
     srt = np.sort(ref, axis=1)
     decided = (srt[:, -1] - srt[:, -2]) > 2 * bound
     np.testing.assert_array_equal(at[decided], np.argmax(ref, axis=1)[decided])
+    np.testing.assert_array_equal(a2[decided], np.argmax(ref, axis=1)[decided])
 
 
-def test_conv_tc_intermediate_activations(ctx, host_noise):
-    """Layer-by-layer check of the tensor-core convolutions (conv3 output = the 7744-vector fed to the fc layer)."""
+def _s2d_geom(l):
+    """Image geometry of a conv layer's INPUT on the shifted-window path (csrc/conv_s2d.cu: s2d_geom)."""
+    hp = (l.hout - 1) * l.stride + l.ksize
+    W = hp // l.stride
+    cp = l.stride * l.stride * l.cin
+    pixp = (W * W + 7) // 8 * 8
+    return dict(S=l.stride, pad=l.pad, W=W, NG=cp // 8, PIXP=pixp, floats=(cp // 8) * 4 * pixp * 4)
+
+
+def _decode_image(buf, l):
+    """[NG][hi/lo][2 channel quads][PIXP][4] floats -> the NHWC activation [hin, hin, cin] it encodes (hi + lo), and
+    the zero padding it must carry."""
+    g = _s2d_geom(l)
+    img = buf[:g["floats"]].reshape(g["NG"], 2, 2, g["PIXP"], 4).astype(np.float64)
+    full = img[:, 0] + img[:, 1]                                     # [NG][2][PIXP][4]
+    chans = full.transpose(2, 0, 1, 3).reshape(g["PIXP"], g["NG"] * 8)[:g["W"] * g["W"]]      # [pixel][s2d channel]
+    S, W = g["S"], g["W"]
+    grid = chans.reshape(W, W, S, S, l.cin).transpose(0, 2, 1, 3, 4).reshape(W * S, W * S, l.cin)   # padded NHWC
+    inner = grid[g["pad"]:g["pad"] + l.hin, g["pad"]:g["pad"] + l.hin]
+    border = grid.copy()
+    border[g["pad"]:g["pad"] + l.hin, g["pad"]:g["pad"] + l.hin] = 0
+    return inner, float(np.abs(border).max())
+
+
+@pytest.mark.parametrize("conv_tc", [2, 1])
+def test_conv_tc_intermediate_activations(ctx, host_noise, conv_tc):
+    """Layer-by-layer check of the tensor-core convolutions (conv3 output = the 7744-vector fed to the fc layer).
+    conv_tc = 2: shifted-window kernels -- conv1 / conv2 write the NEXT layer's space-to-depth image (TF32 hi/lo planes,
+    zero padded), decoded here; conv_tc = 1: NHWC activations of the im2col-staged kernels."""
     net, net_o = N.make_net("LargeModel"), O.make_net("LargeModel")
     P = net.num_params
     rs = np.random.RandomState(8)
@@ -96,22 +126,31 @@ def test_conv_tc_intermediate_activations(ctx, host_noise):
     idx = np.array([17, 17], dtype=np.int64)
     scale = np.array([0.02, -0.02], dtype=np.float32)
     obs = rs.randint(0, 256, size=(2, 84, 84, 4)).astype(np.uint8)
-    sf = SlotForward(ctx, net, 2)
-    sf.set_slots(idx, scale)
-    d_theta, d_obs = cuda(theta), cuda(obs)
-    sf.forward(d_theta, d_obs, paired=True)
-    torch.cuda.synchronize()
+    F.check(F.lib().dne_set_option(b"conv_tc", conv_tc))
+    try:
+        sf = SlotForward(ctx, net, 2)
+        sf.set_slots(idx, scale)
+        d_theta, d_obs = cuda(theta), cuda(obs)
+        sf.forward(d_theta, d_obs, paired=True)
+        torch.cuda.synchronize()
+    finally:
+        F.check(F.lib().dne_set_option(b"conv_tc", 2))
     ws = sf.ws.view(torch.float32)
     off = 0
     for li, l in enumerate(net.layers[:3]):
-        elems = l.out_elems
-        got = ws[off:off + 2 * elems].cpu().numpy().reshape(2, l.hout, l.hout, l.cout)
-        off += ((2 * elems * 4 + 255) // 256 * 256) // 4
+        nxt = net.layers[li + 1]
+        per_slot = max(l.out_elems, _s2d_geom(nxt)["floats"]) if nxt.kind == F.CONV else l.out_elems
+        raw = ws[off:off + 2 * per_slot].cpu().numpy().reshape(2, per_slot)
+        off += ((2 * per_slot * 4 + 255) // 256 * 256) // 4
         for s in range(2):
             th = O.perturb(theta, host_noise, 17, 0.02, 1 if s == 0 else -1)
-            acts = O.forward(net_o, th, obs[s:s + 1], return_all=True)[2]
-            want = acts[li][0]
-            assert np.abs(got[s] - want).max() <= 2e-5 * max(1.0, np.abs(want).max()), (li, s)
+            want = O.forward(net_o, th, obs[s:s + 1], return_all=True)[2][li][0]
+            if conv_tc == 2 and nxt.kind == F.CONV:
+                got, border = _decode_image(raw[s], nxt)
+                assert border == 0.0, (li, s, border)
+            else:
+                got = raw[s][:l.out_elems].reshape(l.hout, l.hout, l.cout)
+            assert np.abs(got - want).max() <= 2e-5 * max(1.0, np.abs(want).max()), (li, s, np.abs(got - want).max())
 
 
 @pytest.mark.parametrize("paired", [0, 2])
