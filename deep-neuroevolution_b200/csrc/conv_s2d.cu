@@ -36,10 +36,22 @@
 
 using namespace tc05;
 
+#ifdef DNE_S2D_TRACE       // dev timeline of CTA 0 (make EXTRA=-DDNE_S2D_TRACE OUT=...; tools/s2d_trace.py); never in the product build
+__device__ long long g_s2d_trace[3][512];
+extern "C" int dne_debug_s2d_trace(long long* host_out) {
+    return cudaMemcpyFromSymbol(host_out, g_s2d_trace, sizeof(g_s2d_trace)) == cudaSuccess ? 0 : -3;
+}
+#define S2D_TR(cond, i) do { if (blockIdx.x == 0 && (cond) && (i) < 512) g_s2d_trace[TRL][(i)] = clock64(); } while (0)
+#define S2D_EV(it, g, e) (16 + (((it) * 16 + (g)) * 8 + (e)))
+#else
+#define S2D_TR(cond, i) do { } while (0)
+#define S2D_EV(it, g, e) 0
+#endif
+
 namespace {
 
 constexpr int S2D_STAGE_WARPS = 8;                         // B (and uint8 A) staging
-constexpr int S2D_EPI_WARPS = 4;                           // one per TMEM lane quarter
+constexpr int S2D_EPI_WARPS = 8;                           // two per TMEM lane quarter (they split the column groups)
 constexpr int S2D_STAGE_THREADS = S2D_STAGE_WARPS * 32;
 constexpr int S2D_EPI_THREADS = S2D_EPI_WARPS * 32;
 constexpr int S2D_THREADS = S2D_STAGE_THREADS + S2D_EPI_THREADS + 96;   // + MMA warp + image producer warp + weight producer warp
@@ -122,9 +134,13 @@ conv_s2d_kernel(SlotArgs sa, int64_t off_w, LayerEpi epi, const void* __restrict
     __shared__ uint64_t a_full[NG], a_empty[NG], raw_full[NSTB], b_full[NSTB], b_empty[NSTB], acc_full[2], acc_empty[2];
     __shared__ uint64_t frame_full[2], frame_empty[2];
     __shared__ uint32_t tmem_base_s;
-    __shared__ ChanEpi epi_s[COUT];
+    __shared__ __align__(16) float s_bias[COUT], s_mean[COUT], s_inv[COUT], s_gamma[COUT], s_beta[COUT];   // per-channel epilogue
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+#ifdef DNE_S2D_TRACE
+    constexpr int TRL = IN_U8 ? 0 : (KS == 4 ? 1 : 2);
+#endif
+    S2D_TR(tid == 0, 0);
     const uint32_t sA = smem_u32(smem), sB = sA + Cfg::A_REGION;
     uint8_t* const gB = smem + Cfg::A_REGION;                                    // generic view of the ring (bulk copies)
     uint8_t* const gFrame = gB + NSTB * Cfg::BST_BYTES;
@@ -150,14 +166,11 @@ conv_s2d_kernel(SlotArgs sa, int64_t off_w, LayerEpi epi, const void* __restrict
         }
         fence_mbar_init();
     }
-    // zero the image region once: the uint8 variant relies on the zero padding never being overwritten, and the slack
-    // behind the last plane (read only into junk rows) must at least not hold stale NaN patterns
-    for (int i = tid; i < Cfg::A_REGION / 16; i += S2D_THREADS) sts128(sA + i * 16, make_float4(0.f, 0.f, 0.f, 0.f));
-    fence_proxy_async_smem();
     fence_before_thread_sync();
     __syncthreads();
     fence_after_thread_sync();
     const uint32_t tmem_base = tmem_base_s;
+    S2D_TR(tid == 0, 1);
 
     if (warp == S2D_STAGE_WARPS + S2D_EPI_WARPS) {
         // ================= MMA warp: converged loop, one elected lane issues (tc05.cuh: elect_one) =================
@@ -173,7 +186,9 @@ conv_s2d_kernel(SlotArgs sa, int64_t off_w, LayerEpi epi, const void* __restrict
             for (int g = 0; g < NG; ++g, ++cb) {
                 const uint32_t st = cb % NSTB;
                 mbar_wait(&a_full[g], it & 1);
+                S2D_TR(lane == 0 && it < 2, S2D_EV(it, g, 4));
                 mbar_wait(&b_full[st], (cb / NSTB) & 1);
+                S2D_TR(lane == 0 && it < 2, S2D_EV(it, g, 5));
                 fence_after_thread_sync();
                 if (elect_one()) {
                     const uint64_t dAg = dA0 + (uint64_t)((g * Cfg::GROUP_BYTES) >> 4);
@@ -195,6 +210,7 @@ conv_s2d_kernel(SlotArgs sa, int64_t off_w, LayerEpi epi, const void* __restrict
                     if (g == NG - 1) mma_commit(&acc_full[buf]);
                 }
                 __syncwarp();
+                S2D_TR(lane == 0 && it < 2, S2D_EV(it, g, 6));
             }
             ++it;
         }
@@ -234,6 +250,7 @@ conv_s2d_kernel(SlotArgs sa, int64_t off_w, LayerEpi epi, const void* __restrict
                 for (int g = 0; g < NG; ++g, ++cb) {
                     const uint32_t st = cb % NSTB;
                     mbar_wait(&b_empty[st], ((cb / NSTB) & 1) ^ 1);
+                    S2D_TR(cb < 2 * NG, S2D_EV(cb / NG, g, 0));
                     mbar_arrive_expect_tx(&raw_full[st], Cfg::RAW_BYTES);
                     uint8_t* dst = gB + st * Cfg::BST_BYTES;
                     const int cp = 8 * g, pp = cp / CIN, ci = cp % CIN, py = pp / S, px = pp % S;
@@ -244,6 +261,7 @@ conv_s2d_kernel(SlotArgs sa, int64_t off_w, LayerEpi epi, const void* __restrict
                         bulk_g2s(dst + tap * Cfg::PIECE_STRIDE, th + (int64_t)kk * COUT - a_t, Cfg::PIECE_STRIDE, &raw_full[st]);
                         bulk_g2s(dst + (NTAP + tap) * Cfg::PIECE_STRIDE, nz + (int64_t)kk * COUT - a_n, Cfg::PIECE_STRIDE, &raw_full[st]);
                     }
+                    S2D_TR(cb < 2 * NG, S2D_EV(cb / NG, g, 1));
                 }
             }
         }
@@ -252,6 +270,15 @@ conv_s2d_kernel(SlotArgs sa, int64_t off_w, LayerEpi epi, const void* __restrict
         // =================                  (first layer: also the uint8 frame -> image planes)       =================
         constexpr int TG = Cfg::TG, NGRP = Cfg::NGRP;
         const int grp = warp / Cfg::WPG, tg = tid - grp * TG;
+        // zero fill, once: the uint8 variant relies on the zero padding of its image never being overwritten (the
+        // converter warps are its only writers); the TMA-fed variants only need finite values in the slack behind the last
+        // plane, which is read into junk accumulator rows.  Only the converter warps wait for it.
+        {
+            constexpr int Z0 = IN_U8 ? 0 : Cfg::IMG_BYTES, Z1 = Cfg::A_REGION;
+            for (int i = Z0 / 16 + tid; i < Z1 / 16; i += S2D_STAGE_THREADS) sts128(sA + i * 16, make_float4(0.f, 0.f, 0.f, 0.f));
+            fence_proxy_async_smem();
+            named_bar_sync(5, S2D_STAGE_THREADS);
+        }
         const int n = tg % COUT;                                 // this thread's output channel in every unit
         constexpr int KQ_STEP = TG / COUT;
         const int kq0 = tg / COUT;
@@ -289,7 +316,9 @@ conv_s2d_kernel(SlotArgs sa, int64_t off_w, LayerEpi epi, const void* __restrict
                         if (g + NGRP >= NG) mbar_arrive(&frame_empty[it & 1]);     // this warp's last read of the raw frame
                     }
                 }
+                S2D_TR(tg == 0 && it < 2, S2D_EV(it, g, 7));
                 mbar_wait(&raw_full[st], (cb / NSTB) & 1);
+                S2D_TR(tg == 0 && it < 2, S2D_EV(it, g, 2));
                 const uint32_t sBs = sB + st * Cfg::BST_BYTES;
                 float w[Cfg::B_UPT][4];
 #pragma unroll
@@ -319,21 +348,29 @@ conv_s2d_kernel(SlotArgs sa, int64_t off_w, LayerEpi epi, const void* __restrict
                 fence_proxy_async_smem();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&b_full[st]);
+                S2D_TR(tg == 0 && it < 2, S2D_EV(it, g, 3));
             }
             ++it;
         }
     } else {
         // ================= epilogue warps: TMEM -> (/255) + bias (+BN) + activation -> global =================
-        const int ew = warp - S2D_STAGE_WARPS;                   // == TMEM lane quarter (warp % 4 == ew)
+        // warp ew: TMEM lane quarter ew & 3 (== warp % 4, the hardware rule), column-group parity ew >> 2
+        const int ew = warp - S2D_STAGE_WARPS, lq = ew & 3, half = ew >> 2;
         const int et = tid - S2D_STAGE_THREADS;
         constexpr float IN_SCALE = IN_U8 ? (1.0f / 255.0f) : 1.0f;
+        constexpr int NJ = COUT / 16;
+        const int act = epi.act;
+        const bool bn = epi.bn == DNE_BN_TF;
         uint32_t it = 0;
         for (int slot = blockIdx.x; slot < n_slots; slot += gridDim.x) {
             if (!slot_active(sa, slot)) continue;
             const float* th = slot_theta(sa, slot);
             const int64_t idx = sa.noise_idx[slot];
             const float s = sa.scale[slot];
-            for (int c = et; c < COUT; c += S2D_EPI_THREADS) epi_s[c] = make_chan_epi(sa, epi, slot, COUT, c, th, idx, s);
+            for (int c = et; c < COUT; c += S2D_EPI_THREADS) {
+                const ChanEpi ce = make_chan_epi(sa, epi, slot, COUT, c, th, idx, s);
+                s_bias[c] = ce.bias; s_mean[c] = ce.mean; s_inv[c] = ce.inv; s_gamma[c] = ce.gamma; s_beta[c] = ce.beta;
+            }
             float* outp = so.base + slot * so.slot_stride;
             if (so.next_img) {
                 // zero padding of the next layer's image: pixels (Y, X) of its padded grid that no output maps to
@@ -350,40 +387,45 @@ conv_s2d_kernel(SlotArgs sa, int64_t off_w, LayerEpi epi, const void* __restrict
                     }
                 }
             }
-            named_bar_sync(2, S2D_EPI_THREADS);                  // epi_s ready
+            named_bar_sync(2, S2D_EPI_THREADS);                  // per-channel parameters ready
             const uint32_t buf = it & 1;
             mbar_wait(&acc_full[buf], (it >> 1) & 1);
+            S2D_TR(et == 0 && it < 2, 2 + it);
             fence_after_thread_sync();
-            const uint32_t t0 = tmem_base + buf * Cfg::ACC_COLS + ((uint32_t)(ew * 32) << 16);
+            const uint32_t t0 = tmem_base + buf * Cfg::ACC_COLS + ((uint32_t)(lq * 32) << 16);
 #pragma unroll 1
-            for (int mt = 0; mt < MT; ++mt) {
-                const int m = mt * 128 + ew * 32 + lane;
+            for (int q = half; q < MT * NJ; q += 2) {             // (M tile, 16-column group) work items of this warp
+                const int mt = q / NJ, n0 = (q - mt * NJ) * 16;
+                const int m = mt * 128 + lq * 32 + lane;
                 const int oy = m / W, ox = m - oy * W;
                 const bool valid = (oy < HOUT) && (ox < HOUT);
-                int pix = 0, pp = 0;
-                if (so.next_img) {
-                    const int Y = oy + so.nPADB, X = ox + so.nPADB;
-                    pix = (Y / so.nS) * so.nW + (X / so.nS);
-                    pp = (Y % so.nS) * so.nS + (X % so.nS);
-                }
+                float v[16], v2[16];
+                __syncwarp();                                    // tcgen05.ld is .sync.aligned: the warp must be converged
+                tmem_ld16_async(t0 + (uint32_t)(mt * 2 * COUT + n0), v);
+                tmem_ld16_async(t0 + (uint32_t)(mt * 2 * COUT + COUT + n0), v2);
+                tmem_ld_wait();
+                if (valid) {
 #pragma unroll
-                for (int n0 = 0; n0 < COUT; n0 += 16) {
-                    float v[16], v2[16];
-                    __syncwarp();                                // tcgen05.ld is .sync.aligned: the warp must be converged
-                    tmem_ld16(t0 + (uint32_t)(mt * 2 * COUT + n0), v);
-                    tmem_ld16(t0 + (uint32_t)(mt * 2 * COUT + COUT + n0), v2);
-                    if (valid) {
+                    for (int x = 0; x < 16; x += 4) {
+                        const float4 b4 = *reinterpret_cast<const float4*>(&s_bias[n0 + x]);
+                        const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
-                    for (int x = 0; x < 16; ++x) {
-                        float y = v[x] + v2[x];
-                        if (IN_U8) y *= IN_SCALE;
-                        v[x] = epi_s[n0 + x].apply(y);
+                        for (int y = 0; y < 4; ++y) {
+                            float r = __uint_as_float(__float_as_uint(v[x + y])) + v2[x + y];
+                            if (IN_U8) r *= IN_SCALE;
+                            r += bb[y];
+                            if (bn) r = (r - s_mean[n0 + x + y]) * s_inv[n0 + x + y] * s_gamma[n0 + x + y] + s_beta[n0 + x + y];   // policies.py:322
+                            v[x + y] = act == DNE_ACT_RELU ? fmaxf(r, 0.0f) : (act == DNE_ACT_TANH ? tanhf(r) : r);
+                        }
                     }
                     if (!so.next_img) {
                         float4* dst = reinterpret_cast<float4*>(outp + (int64_t)(oy * HOUT + ox) * COUT + n0);
 #pragma unroll
                         for (int x = 0; x < 16; x += 4) dst[x / 4] = make_float4(v[x], v[x + 1], v[x + 2], v[x + 3]);
                     } else {
+                        const int Y = oy + so.nPADB, X = ox + so.nPADB;
+                        const int pix = (Y / so.nS) * so.nW + (X / so.nS);
+                        const int pp = (Y % so.nS) * so.nS + (X % so.nS);
 #pragma unroll
                         for (int x = 0; x < 16; x += 4) {
                             const int cq = pp * (COUT / 4) + (n0 + x) / 4;
@@ -397,18 +439,19 @@ conv_s2d_kernel(SlotArgs sa, int64_t off_w, LayerEpi epi, const void* __restrict
                             p[(size_t)2 * so.nPIXP] = lo;
                         }
                     }
-                    }
                 }
             }
             fence_before_thread_sync();
             __syncwarp();
             if (lane == 0) mbar_arrive(&acc_empty[buf]);
-            named_bar_sync(2, S2D_EPI_THREADS);                  // epi_s reusable
+            S2D_TR(et == 0 && it < 2, 4 + it);
+            named_bar_sync(2, S2D_EPI_THREADS);                  // per-channel parameters reusable
             ++it;
         }
     }
     fence_before_thread_sync();
     __syncthreads();
+    S2D_TR(tid == 0, 6);
     if (warp == 0) tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
 }
 

@@ -445,10 +445,11 @@ dense_small_kernel(SlotArgs sa, int64_t off_w, LayerEpi epi, const float* __rest
 }
 
 // combine + output head in one kernel (one CTA per slot): the hidden vector y[N1] of dense_combine_kernel is built in
-// shared memory and fed straight to the head of dense_small_kernel (512x18 / 256x18 / 256x17) and its argmax -- one launch
-// and one global round trip less per tick.  Same per-element arithmetic and summation order as the two separate kernels.
-constexpr int DCH_MAXK = 1024;
-__global__ void __launch_bounds__(DS_THREADS)
+// shared memory and fed straight to the head (512x18 / 256x18 / 256x17) and its argmax -- one launch and one global round
+// trip less per tick.  Both phases are latency bound (L2 partials; theta + noise rows of the head), so every thread keeps 8
+// independent loads in flight and adds them in index order (the sums are order-deterministic).
+constexpr int DCH_MAXK = 1024, DCH_THREADS = 512, DCH_B = 8;
+__global__ void __launch_bounds__(DCH_THREADS)
 dense_combine_head_kernel(SlotArgs sa, LayerEpi epi1, int n_slots, int N1, int G, const float* __restrict__ part_theta,
                           int n_split, int Gt, const float* __restrict__ part_noise, int n_chunks,
                           float* __restrict__ hidden_out, int64_t hidden_stride,
@@ -457,52 +458,73 @@ dense_combine_head_kernel(SlotArgs sa, LayerEpi epi1, int n_slots, int N1, int G
     const int slot = blockIdx.x;
     if (!slot_active(sa, slot)) return;
     __shared__ float xs[DCH_MAXK];
-    __shared__ float red[DS_THREADS];
+    __shared__ float red[DCH_THREADS];
     __shared__ float ys[DS_MAXN];
     const int t = threadIdx.x;
     const float* th = slot_theta(sa, slot);
     const int64_t idx = sa.noise_idx[slot];
     const float s = sa.scale[slot];
     // ---- phase 1: y = act(bn(sum_split Ytheta + s * sum_chunk Ynoise + bias))  (dense_combine_kernel) ----
-    for (int n = t; n < N1; n += DS_THREADS) {
+    for (int n = t; n < N1; n += DCH_THREADS) {
+        const float* pt;
+        int64_t pt_stride;
+        if (Gt == 0) { pt = part_theta + (int64_t)slot * N1 + n; pt_stride = (int64_t)n_slots * N1; }
+        else { pt = part_theta + (((int64_t)(slot / Gt) * n_split) * Gt + (slot % Gt)) * N1 + n; pt_stride = (int64_t)Gt * N1; }
         float yt = 0.0f;
-        if (Gt == 0) {
-            for (int sp = 0; sp < n_split; ++sp) yt += part_theta[((int64_t)sp * n_slots + slot) * N1 + n];
-        } else {
-            const float* pt = part_theta + (((int64_t)(slot / Gt) * n_split) * Gt + (slot % Gt)) * N1 + n;
-            for (int c = 0; c < n_split; ++c) yt += pt[(int64_t)c * Gt * N1];
+        int c = 0;
+        for (; c + DCH_B <= n_split; c += DCH_B) {
+            float p[DCH_B];
+#pragma unroll
+            for (int j = 0; j < DCH_B; ++j) p[j] = pt[(int64_t)(c + j) * pt_stride];
+#pragma unroll
+            for (int j = 0; j < DCH_B; ++j) yt += p[j];
         }
+        for (; c < n_split; ++c) yt += pt[(int64_t)c * pt_stride];
         const int group = slot / G, g = slot % G;
-        float yn = 0.0f;
         const float* pn = part_noise + (((int64_t)group * n_chunks) * G + g) * N1 + n;
-        for (int c = 0; c < n_chunks; ++c) yn += pn[(int64_t)c * G * N1];
+        const int64_t pn_stride = (int64_t)G * N1;
+        float yn = 0.0f;
+        for (c = 0; c + DCH_B <= n_chunks; c += DCH_B) {
+            float p[DCH_B];
+#pragma unroll
+            for (int j = 0; j < DCH_B; ++j) p[j] = pn[(int64_t)(c + j) * pn_stride];
+#pragma unroll
+            for (int j = 0; j < DCH_B; ++j) yn += p[j];
+        }
+        for (; c < n_chunks; ++c) yn += pn[(int64_t)c * pn_stride];
         const ChanEpi ce = make_chan_epi(sa, epi1, slot, N1, n, th, idx, s);
         const float y = ce.apply(fmaf(s, yn, yt));
         xs[n] = y;
         if (hidden_out) hidden_out[(int64_t)slot * hidden_stride + n] = y;
     }
     __syncthreads();
-    // ---- phase 2: the head (dense_small_kernel) on x = xs ----
+    // ---- phase 2: the head on x = xs.  Thread t < RG*N owns output column n = t % N and row group rg = t / N; one batch
+    // covers DCH_B*RG consecutive rows = contiguous weights, so the theta / noise loads are flat and coalesced ----
     const int K = N1, N = N2;
-    const int RG = DS_THREADS / N;
+    const int RG = DCH_THREADS / N;
     const int n = t % N, rg = t / N;
     const float* tw = th + off_w2;
     const float* nz = sa.noise + idx + off_w2;
-    float acc0 = 0.0f, acc1 = 0.0f;
+    float acc = 0.0f;
     if (rg < RG) {
         int k = rg;
-        for (; k + RG < K; k += 2 * RG) {
-            const int64_t f0 = (int64_t)k * N + n, f1 = (int64_t)(k + RG) * N + n;
-            const float t0 = tw[f0], n0 = nz[f0], t1 = tw[f1], n1 = nz[f1];
-            acc0 = fmaf(xs[k], perturbed(t0, s, n0), acc0);
-            acc1 = fmaf(xs[k + RG], perturbed(t1, s, n1), acc1);
+        for (; k + (DCH_B - 1) * RG < K; k += DCH_B * RG) {
+            float a[DCH_B], b[DCH_B];
+#pragma unroll
+            for (int j = 0; j < DCH_B; ++j) {
+                const int64_t f = (int64_t)(k + j * RG) * N + n;
+                a[j] = tw[f];
+                b[j] = nz[f];
+            }
+#pragma unroll
+            for (int j = 0; j < DCH_B; ++j) acc = fmaf(xs[k + j * RG], perturbed(a[j], s, b[j]), acc);
         }
-        if (k < K) {
-            const int64_t f0 = (int64_t)k * N + n;
-            acc0 = fmaf(xs[k], perturbed(tw[f0], s, nz[f0]), acc0);
+        for (; k < K; k += RG) {
+            const int64_t f = (int64_t)k * N + n;
+            acc = fmaf(xs[k], perturbed(tw[f], s, nz[f]), acc);
         }
     }
-    red[t] = acc0 + acc1;
+    red[t] = acc;
     __syncthreads();
     if (t < N) {
         float sum = 0.0f;
@@ -660,8 +682,7 @@ DensePlan dne_plan_dense(const dne_layer_desc& L, int n_slots, int paired, bool 
 }
 
 bool dne_head_fusable(const dne_layer_desc& L, const DensePlan& p, const dne_layer_desc& head, const DensePlan& hp) {
-    return p.decomposed && !hp.decomposed && L.cout <= DCH_MAXK && head.cin == L.cout && head.cout <= DS_MAXN &&
-           head.cout <= DS_THREADS;
+    return p.decomposed && !hp.decomposed && L.cout <= DCH_MAXK && head.cin == L.cout && head.cout <= DS_MAXN;
 }
 
 int dne_launch_dense_layer(const dne_ctx* ctx, const SlotArgs& sa, const dne_layer_desc& L, const LayerEpi& epi,
@@ -737,7 +758,7 @@ int dne_launch_dense_layer(const dne_ctx* ctx, const SlotArgs& sa, const dne_lay
         }
     }
     if (head) {          // combine + output head + argmax in one kernel (the hidden vector stays in shared memory)
-        dense_combine_head_kernel<<<n_slots, DS_THREADS, 0, st>>>(
+        dense_combine_head_kernel<<<n_slots, DCH_THREADS, 0, st>>>(
             sa, epi, n_slots, N, p.G, part_theta, p.n_split, p.Gt, part_noise, p.n_chunks, out, out_slot_stride,
             head->L->off_w, head->epi, head->L->cout, head->out, head->out_slot_stride, head->actions);
     } else {

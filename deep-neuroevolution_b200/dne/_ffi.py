@@ -55,6 +55,8 @@ _SIGS = {
     "dne_vbn_reference_pass": [_P, C.POINTER(NetDesc), _P, _P, _P, _P, _P, C.c_int, _P, C.c_int, _P, _P,
                                C.c_size_t, _P],
     "dne_preprocess_atari": [_P, _P, _P, _P, C.c_int, C.c_int, _P],
+    "dne_warp_atari_rgb": [_P, _P, C.c_int, _P],
+    "dne_warp_atari_palette": [_P, _P, _P, _P, C.c_int, _P],
     "dne_centered_rank": [_P, C.c_int, _P, _P, _P],
     "dne_es_grad": [_P, _P, _P, C.c_int, C.c_int64, C.c_double, _P, C.c_int, _P],
     "dne_adam_step": [_P, _P, _P, _P, _P, C.c_int64, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double,

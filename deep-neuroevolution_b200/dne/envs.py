@@ -157,11 +157,38 @@ class SyntheticVectorEnv(BatchEnv):
         return rs.uniform(-0.4, 0.4, size=(k, self.action_space.shape[0])).astype(np.float32)
 
 
-def make_env(env_id: str, n_slots: int, seed: int = 0, episode_len=None, **kw) -> BatchEnv:
-    """``gym.make(exp['env_id'])`` (es.py:131) for a whole slot table.  Only the synthetic stubs exist in this image;
-    a real ALE / MuJoCo backend registers itself here."""
-    if env_id.endswith("NoFrameskip-v4") or env_id.startswith("Synthetic") and "Atari" in env_id:
-        return SyntheticAtariEnv(n_slots, episode_len=episode_len if episode_len is not None else 1000, seed=seed, **kw)
-    if env_id.startswith("Humanoid") or env_id.startswith("SyntheticVector"):
-        return SyntheticVectorEnv(n_slots, episode_len=episode_len if episode_len is not None else 1000, seed=seed, **kw)
-    raise KeyError(f"no environment backend for {env_id!r} in this build (gym/ALE/MuJoCo are not vendored)")
+def make_env(env_id: str, n_slots: int, seed: int = 0, episode_len=None, allow_synthetic: bool = False, **kw) -> BatchEnv:
+    """``gym.make(exp['env_id'])`` (es.py:131) for a whole slot table.
+
+    ALE / gym / MuJoCo are not vendored by the reference and are absent from this image, so the only backends here are
+    the synthetic stubs.  They are returned for the explicit ids ``SyntheticAtari*`` / ``SyntheticVector*``; for a REAL id
+    (``FrostbiteNoFrameskip-v4``, ``Humanoid-v1`` ...) they are returned only when the caller opts in
+    (``exp['allow_synthetic_env'] = true`` or ``DNE_ALLOW_SYNTHETIC_ENV=1``), with a loud warning -- a run that silently
+    optimised random frames while logging and snapshotting like a real one would be worse than an error.  A real emulator
+    backend registers itself in ``ENV_BACKENDS`` (id prefix -> factory)."""
+    import logging
+    import os
+    for prefix, factory in ENV_BACKENDS.items():
+        if env_id.startswith(prefix):
+            return factory(env_id, n_slots, seed=seed, episode_len=episode_len, **kw)
+    atari = env_id.endswith("NoFrameskip-v4") or env_id.startswith("SyntheticAtari")
+    vector = env_id.startswith("Humanoid") or env_id.startswith("SyntheticVector")
+    if not (atari or vector):
+        raise KeyError(f"no environment backend for {env_id!r} in this build (gym/ALE/MuJoCo are not vendored)")
+    if not env_id.startswith("Synthetic"):
+        if not (allow_synthetic or os.environ.get("DNE_ALLOW_SYNTHETIC_ENV") == "1"):
+            raise KeyError(f"no real environment backend for {env_id!r} in this build (gym/ALE/MuJoCo are not vendored); "
+                           "register one in dne.envs.ENV_BACKENDS, or opt in to the synthetic stand-in with "
+                           "exp['allow_synthetic_env'] = true / DNE_ALLOW_SYNTHETIC_ENV=1")
+        logging.getLogger(__name__).warning(
+            "SYNTHETIC ENVIRONMENT standing in for %r: observations are random frames / vectors and rewards are Bernoulli "
+            "noise -- throughput measurements only, NOT training on the real task", env_id)
+    if atari:
+        env = SyntheticAtariEnv(n_slots, episode_len=episode_len if episode_len is not None else 1000, seed=seed, **kw)
+    else:
+        env = SyntheticVectorEnv(n_slots, episode_len=episode_len if episode_len is not None else 1000, seed=seed, **kw)
+    env.synthetic = True
+    return env
+
+
+ENV_BACKENDS = {}        # id prefix -> factory(env_id, n_slots, seed=, episode_len=, **kw) -> BatchEnv (real emulators plug in here)

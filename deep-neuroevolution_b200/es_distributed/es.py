@@ -144,7 +144,7 @@ def setup(exp, single_threaded, n_slots=256, env=None, seed=None):
     config = Config(**exp['config'])
     if env is None:
         env = make_env(exp['env_id'], n_slots, seed=0 if seed is None else seed,
-                       episode_len=exp.get('synthetic_episode_len'))
+                       episode_len=exp.get('synthetic_episode_len'), allow_synthetic=bool(exp.get('allow_synthetic_env')))
     policy = getattr(policies, exp['policy']['type'])(env.observation_space, env.action_space, **exp['policy']['args'],
                                                      seed=seed)
     return config, env, None, policy

@@ -165,6 +165,19 @@ int dne_vbn_reference_pass(dne_ctx* ctx, const dne_net_desc* net, const float* d
 int dne_preprocess_atari(const uint8_t* d_prev, const uint8_t* d_cur, uint8_t* d_stack,
                          const uint8_t* d_reset_mask, int n_slots, int mode, void* stream);
 
+/* The 210x160 -> 84x84 warp in front of the frame stack, both reference flavours (one 84x84 frame per raw frame pair):
+ * dne_warp_atari_rgb      atari_wrappers.py:105,138-142: d_raw uint8 [n, 2, 210, 160, 3] (the last two RGB frames) ->
+ *                         per-channel max -> gray float32 -> PIL BILINEAR (area-scaled triangle filter, two passes, double
+ *                         accumulation) -> uint8 [n, 84, 84] (truncating cast).  Bit-exact with Pillow on the same gray.
+ * dne_warp_atari_palette  tf_atari.py:88-92,149: d_raw uint8 [n, 2, 210, 160] NTSC palette indices, d_gray_lut float[256]
+ *                         -> max of the two gray frames -> resize_bilinear(align_corners=True) -> float32 [n, 84, 84]
+ *                         (d_out_f32, nullable) and / or its uint8 quantisation round(255*x) (d_out_u8, nullable) for
+ *                         the uint8 frame-stack pipeline.
+ * Feed the result to dne_preprocess_atari with d_prev = NULL (the max has already been taken on the raw frames). */
+int dne_warp_atari_rgb(const uint8_t* d_raw, uint8_t* d_out, int n_frames, void* stream);
+int dne_warp_atari_palette(const uint8_t* d_raw, const float* d_gray_lut, float* d_out_f32, uint8_t* d_out_u8,
+                           int n_frames, void* stream);
+
 /* ---- update side -------------------------------------------------------------------------------- */
 /* compute_ranks / compute_centered_ranks (es.py:70-85) over the flattened returns; stable tie rule. */
 int dne_centered_rank(const float* d_returns, int count, float* d_centered, int32_t* d_ranks, void* stream);

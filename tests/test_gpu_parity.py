@@ -388,3 +388,108 @@ def test_errors_are_reported_not_fatal(ctx):
     assert rc == -1 and b"null" in L.dne_last_error()
     with pytest.raises(F.DneError):
         F.ptr(torch.zeros(4))            # CPU tensor: no CPU fallback
+
+
+# ---- pins against fixtures generated from the reference's own expressions (tests/golden/make_golden_nses_ga.py) ---------
+@pytest.fixture(scope="module")
+def golden2():
+    import os
+    return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_nses_ga.npz"))
+
+
+def test_knn_novelty_vs_reference_nses(ctx, golden2):
+    """dne_knn_novelty against es_distributed/nses.py:12-32 itself (recorded with a stub tensorflow): ragged BC
+    sequences, k below / at / above the archive size, archive smaller than k."""
+    L = F.lib()
+    qp, ql, ap, al = golden2["nov_q_pad"], golden2["nov_q_len"], golden2["nov_a_pad"], golden2["nov_a_len"]
+    q, A, t_max, D = len(ql), len(al), qp.shape[1], qp.shape[2]
+    nb = C.c_size_t()
+    F.check(L.dne_knn_ws_bytes(q, A, C.byref(nb)))
+    ws = torch.empty(nb.value, dtype=torch.uint8, device=DEV)
+    nov = torch.empty(q, dtype=torch.float32, device=DEV)
+    d_qp, d_ql, d_ap, d_al = cuda(qp), cuda(ql), cuda(ap), cuda(al)
+    for k in (1, 10, 19, 40):
+        F.check(L.dne_knn_novelty(F.ptr(d_qp), F.ptr(d_ql), q, F.ptr(d_ap), F.ptr(d_al), A, t_max, D, k, F.ptr(nov),
+                                  F.ptr(ws), ws.numel(), F.stream_ptr()))
+        np.testing.assert_allclose(nov.cpu().numpy(), golden2[f"nov_k{k}"].astype(np.float32), rtol=1e-6)
+    F.check(L.dne_knn_novelty(F.ptr(d_qp), F.ptr(d_ql), q, F.ptr(d_ap), F.ptr(d_al), 3, t_max, D, 10, F.ptr(nov),
+                              F.ptr(ws), ws.numel(), F.stream_ptr()))
+    np.testing.assert_allclose(nov.cpu().numpy(), golden2["nov_k10_arch3"].astype(np.float32), rtol=1e-6)
+
+
+@pytest.mark.parametrize("pop,T", [(1000, 20), (64, 64), (7, 3)])
+def test_ga_truncate_vs_reference_argpartition(golden2, pop, T):
+    """dne_ga_truncate against the literal ga.py:145-149 numpy expression: best individual first, same top-T set."""
+    fit, ref = golden2[f"ga_fit_{pop}_{T}"], golden2[f"ga_sel_{pop}_{T}"]
+    sel = torch.full((T,), -1, dtype=torch.int32, device=DEV)
+    d_fit = cuda(fit)
+    F.check(F.lib().dne_ga_truncate(F.ptr(d_fit), pop, T, F.ptr(sel), F.stream_ptr()))
+    got = sel.cpu().numpy()
+    assert got[0] == ref[0] and set(got.tolist()) == set(ref.tolist())
+    assert (np.diff(fit[got]) <= 0).all()                      # and in descending order (the canonical rule)
+
+
+def test_warp_atari_rgb_vs_pillow(golden2):
+    """dne_warp_atari_rgb (atari_wrappers.py:105,138-142): bit-exact against the oracle (whose resize is pinned bit-exactly
+    to Pillow) on max-of-two-frames inputs, and within the reference's own gray ambiguity (1 ulp -> <= 1 level on < 1 %
+    of the pixels) of the recorded numpy + Pillow output."""
+    rgb = golden2["warp_rgb"]                                   # [6, 210, 160, 3]
+    n = len(rgb)
+    pair_same = np.stack([rgb, rgb], axis=1)                    # max(a, a) = a: comparable with the recorded frames
+    pair_mix = np.stack([rgb, np.roll(rgb, 1, axis=0)], axis=1)
+    for pairs, recorded in ((pair_same, golden2["warp_out"]), (pair_mix, None)):
+        d_raw = cuda(pairs)
+        out = torch.zeros(n, 84, 84, dtype=torch.uint8, device=DEV)
+        F.check(F.lib().dne_warp_atari_rgb(F.ptr(d_raw), F.ptr(out), n, F.stream_ptr()))
+        got = out.cpu().numpy()
+        want = np.stack([O.warp_frame_cpu(np.maximum(p[0], p[1])) for p in pairs])
+        np.testing.assert_array_equal(got, want)
+        if recorded is not None:
+            diff = np.abs(got.astype(np.int32) - recorded.astype(np.int32))
+            assert diff.max() <= 1 and (diff != 0).mean() < 0.01
+
+
+def test_warp_atari_palette_vs_oracle():
+    """dne_warp_atari_palette (tf_atari.py:88-92): LUT gather, max over two frames, align_corners bilinear -- bit-exact
+    against the float32 formula restatement; the uint8 output is its round(255*x) quantisation."""
+    rs = np.random.RandomState(17)
+    pal = O.ntsc_gray_palette()
+    n = 5
+    raw = (rs.randint(0, 128, size=(n, 2, 210, 160)) * 2).astype(np.uint8)
+    d_raw, d_pal = cuda(raw), cuda(pal.astype(np.float32))
+    out_f = torch.zeros(n, 84, 84, dtype=torch.float32, device=DEV)
+    out_u = torch.zeros(n, 84, 84, dtype=torch.uint8, device=DEV)
+    F.check(F.lib().dne_warp_atari_palette(F.ptr(d_raw), F.ptr(d_pal), F.ptr(out_f), F.ptr(out_u), n, F.stream_ptr()))
+    want = np.stack([O.warp_frame_gpu(raw[i], pal) for i in range(n)])
+    np.testing.assert_array_equal(out_f.cpu().numpy(), want)
+    np.testing.assert_array_equal(out_u.cpu().numpy(), np.rint(np.clip(want * np.float32(255.0), 0, 255)).astype(np.uint8))
+    # chained with the frame stack: d_prev = NULL (the max was taken on the raw frames)
+    stack = torch.zeros(n, 84, 84, 4, dtype=torch.uint8, device=DEV)
+    reset = cuda(np.ones(n, dtype=np.uint8))
+    F.check(F.lib().dne_preprocess_atari(None, F.ptr(out_u), F.ptr(stack), F.ptr(reset), n, 1, F.stream_ptr()))
+    got = stack.cpu().numpy()
+    assert (got[..., :3] == 0).all() and np.array_equal(got[..., 3], out_u.cpu().numpy())
+
+
+@pytest.mark.skipif(int(__import__("os").environ.get("DNE_SKIP_FULL_TABLE", "0")) == 1, reason="full 250M-entry table skipped")
+def test_ga_materialize_reference_genome_kat(golden2):
+    """The 260-mutation Frostbite genome shipped with the reference (gpu_implementation/neuroevolution/display.py:31) on
+    the REAL 250,000,000-entry noise table: dne_ga_materialize (mode 0, models/base.py:140-146,155-156) against the
+    recorded theta checksums / sampled coordinates (oracle on the same table, tests/golden/make_golden_nses_ga.py)."""
+    table = SharedNoiseTable(device=DEV)                         # es.py:54-60: seed 123, 250M entries (~20 s)
+    assert table.count == 250_000_000
+    dev = table.device_tensor[:250_000_000:1000].double().sum().item()
+    assert dev == pytest.approx(float(golden2["genome_noise_checksum"]), rel=1e-9)
+    kctx = make_context(0, table)
+    net = N.make_net("LargeModel")
+    seeds = np.concatenate([[int(golden2["genome_idx0"])], golden2["genome_idx"]]).astype(np.int64)
+    powers = np.concatenate([[0.0], golden2["genome_power"]]).astype(np.float32)
+    std = (C.c_double * len(net.layers))(*net.init_std())
+    out = torch.empty(net.num_params, dtype=torch.float32, device=DEV)
+    d_seeds, d_powers = cuda(seeds), cuda(powers)
+    F.check(F.lib().dne_ga_materialize(kctx.handle, C.byref(net.desc), F.ptr(d_seeds), F.ptr(d_powers), len(seeds), std, 0,
+                                       F.ptr(out), F.stream_ptr()))
+    got = out.cpu().numpy()
+    np.testing.assert_array_equal(got[golden2["genome_theta_cols"]], golden2["genome_theta_vals"])
+    assert got.astype(np.float64).sum() == pytest.approx(float(golden2["genome_theta_sum"]), rel=1e-12, abs=1e-9)
+    assert np.square(got.astype(np.float64)).sum() == pytest.approx(float(golden2["genome_theta_sumsq"]), rel=1e-12)
