@@ -129,6 +129,9 @@ def run_b200(args):
     L = F.lib()
     if os.environ.get("DNE_GEMV_CTAS"):
         F.check(L.dne_set_option(b"gemv_ctas_per_sm", int(os.environ["DNE_GEMV_CTAS"])))
+    for kv in filter(None, os.environ.get("DNE_OPTS", "").split(",")):       # dev A/B switches: "name=value,name=value"
+        k, v = kv.split("=")
+        F.check(L.dne_set_option(k.encode(), int(v)))
 
     t0 = time.time()
     noise = SharedNoiseTable(count=args.noise_count, device=dev)
@@ -177,6 +180,12 @@ def run_b200(args):
     stream_ptr = [C.c_void_p(s.cuda_stream) for s in streams]
     ev_ptr = [C.c_void_p(e.cuda_event) for e in phase_ev]
 
+    KERNELS_PER_TICK = 6          # conv1-3, theta GEMM, noise GEMV, combine+head (LargeModel, default options)
+    USE_GRAPH = os.environ.get("DNE_BENCH_GRAPH", "0") == "1"
+    PROF_EVERY = 16 if USE_GRAPH else 1
+    graphs = {}
+    prof_state = {"on": False}
+
     def generation_value():
         idx_all = np.array([noise.sample_index(idx_stream, P) for _ in range(n_pairs)], dtype=np.int64)
         my = idx_all[lo:hi]
@@ -208,16 +217,43 @@ def run_b200(args):
             fwd = L.dne_perturb_forward_conv
             set_ev = L.dne_set_phase_events
             theta_p = F.ptr(upd.theta)
+            for h in live:           # once per theta (the Adam step of the previous generation dropped the prepared entry)
+                with torch.cuda.stream(streams[h]):
+                    sfs[h].prepare(upd.theta, part)
+            def tick(h, r):
+                a = fwd_args[h]
+                rc = fwd(ctx.handle, net_ref, theta_p, a[0], a[1], None, a[2] if part_active[h] else None, part, 1,
+                         obs_ptr[r][h], None, a[3], a[4], a[5], a[6], stream_ptr[h])
+                if rc:
+                    F.check(rc)
             for t in range(T):
                 r = t % R
                 for h in live:
                     if NS >= 2 and PHASED:
                         set_ev(ctx.handle, ev_ptr[(h - 1) % NS], ev_ptr[h], PHASE_MODE)
-                    a = fwd_args[h]
-                    rc = fwd(ctx.handle, net_ref, theta_p, a[0], a[1], None, a[2] if part_active[h] else None, part, 1,
-                             obs_ptr[r][h], None, a[3], a[4], a[5], a[6], stream_ptr[h])
-                    if rc:
-                        F.check(rc)
+                    if USE_GRAPH and (t % PROF_EVERY) != 0:
+                        # the tick's kernel sequence replayed as one CUDA graph (captured once per table / observation
+                        # block / active-mask variant): no per-kernel launch gaps.  Every PROF_EVERY-th tick is launched
+                        # kernel by kernel so that the GEMV of the timed region is still timed with CUDA events.
+                        key = (h, r, part_active[h])
+                        g = graphs.get(key)
+                        if g is None:
+                            L.dne_profile_enable(ctx.handle, 0, 0)
+                            torch.cuda.synchronize()
+                            g = torch.cuda.CUDAGraph()
+                            with torch.cuda.graph(g, stream=streams[h]):
+                                tick(h, r)
+                            graphs[key] = g
+                        with torch.cuda.stream(streams[h]):
+                            g.replay()
+                        tally["graph_kernels"] = tally.get("graph_kernels", 0) + KERNELS_PER_TICK
+                    else:
+                        if USE_GRAPH and prof_state["on"]:
+                            L.dne_profile_enable(ctx.handle, 2, 0)          # resume (keeps the samples taken so far)
+                            tick(h, r)
+                            L.dne_profile_enable(ctx.handle, 0, 0)          # pause: graph replays carry no event records
+                        else:
+                            tick(h, r)
                 ret_acc.add_(rew_pool[t % 64])                     # one bookkeeping op per tick, main stream
             for s in streams:
                 cur.wait_stream(s)
@@ -237,7 +273,11 @@ def run_b200(args):
         torch.cuda.synchronize()
         if profile:
             F.check(L.dne_profile_enable(ctx.handle, 1, 16384))
+            prof_state["on"] = True
+            if USE_GRAPH:
+                F.check(L.dne_profile_enable(ctx.handle, 0, 0))             # paused; resumed around the un-graphed ticks
         L.dne_launch_count(1)
+        tally["graph_kernels"] = 0
         sampler = ClockSampler(local)
         if rank == 0:
             sampler.start()
@@ -251,10 +291,11 @@ def run_b200(args):
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1)
         clocks = sampler.stop() if rank == 0 else None
-        launches = L.dne_launch_count(0)
+        launches = L.dne_launch_count(0) + tally.get("graph_kernels", 0)
         prof = None
         if profile:
             n, tot = C.c_int(), C.c_double()
+            prof_state["on"] = False
             F.check(L.dne_profile_enable(ctx.handle, 0, 0))
             F.check(L.dne_profile_read(ctx.handle, C.byref(n), C.byref(tot)))
             prof = (n.value, tot.value)

@@ -12,6 +12,7 @@
 #error "libdne is written for sm_100a (B200) only"
 #endif
 
+#define DNE_MAX_PREP 16
 struct dne_ctx {
     int device;
     int sm_count;
@@ -26,7 +27,10 @@ struct dne_ctx {
     void* ev_record;        // recorded right before the first HBM-bound noise GEMV of the call
     int ev_record_done;
     int ev_mode;            // 0: wait before the first kernel, record before the GEMV; 1: wait before / record after the GEMV
+    // workspaces whose prepared-theta region (dne_theta_prepare) is current: (workspace, theta it was made from)
+    struct { const void* ws; const float* theta; int n_slots; } prep[DNE_MAX_PREP];
 };
+void dne_prep_invalidate_theta(dne_ctx* ctx, const float* d_theta);   // a kernel of this library is about to rewrite theta
 extern unsigned long long g_dne_launches;   // kernels launched by this library (process-wide)
 #define DNE_LAUNCHED(n) (g_dne_launches += (unsigned long long)(n))
 #define DNE_SCRATCH_DOUBLES 16384

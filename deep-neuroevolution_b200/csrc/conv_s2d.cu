@@ -120,6 +120,8 @@ struct S2dOut {
     int64_t slot_stride;        // floats
     int next_img;               // 0: NHWC [HOUT*HOUT][COUT];  1: image of the next layer (geometry below)
     int nS, nPADB, nW, nPIXP, nHP;
+    float* xc;                  // nullable (NHWC mode only): the same vector as the A operand of the TMA-fed theta GEMM,
+    int xc_kq;                  //   Xc[slot / 128][k quad][hi | lo][slot % 128][4]  (theta_gemm_tma.cu), xc_kq = K / 4
 };
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -422,6 +424,20 @@ conv_s2d_kernel(SlotArgs sa, int64_t off_w, LayerEpi epi, const void* __restrict
                         float4* dst = reinterpret_cast<float4*>(outp + (int64_t)(oy * HOUT + ox) * COUT + n0);
 #pragma unroll
                         for (int x = 0; x < 16; x += 4) dst[x / 4] = make_float4(v[x], v[x + 1], v[x + 2], v[x + 3]);
+                        if (so.xc) {
+                            const int kq0 = ((oy * HOUT + ox) * COUT + n0) >> 2;
+                            float4* xp = reinterpret_cast<float4*>(so.xc) + ((int64_t)(slot >> 7) * so.xc_kq + kq0) * 256 + (slot & 127);
+#pragma unroll
+                            for (int x = 0; x < 16; x += 4) {
+                                float4 hi, lo;
+                                split_tf32_fast(v[x], hi.x, lo.x);
+                                split_tf32_fast(v[x + 1], hi.y, lo.y);
+                                split_tf32_fast(v[x + 2], hi.z, lo.z);
+                                split_tf32_fast(v[x + 3], hi.w, lo.w);
+                                xp[(x / 4) * 256] = hi;
+                                xp[(x / 4) * 256 + 128] = lo;
+                            }
+                        }
                     } else {
                         const int Y = oy + so.nPADB, X = ox + so.nPADB;
                         const int pix = (Y / so.nS) * so.nW + (X / so.nS);
@@ -498,8 +514,10 @@ size_t dne_s2d_image_bytes(const dne_layer_desc& L) {
 // next: the following conv layer if it consumes an image (nullptr: write NHWC floats).
 int dne_launch_conv_layer_s2d(const SlotArgs& sa, const dne_layer_desc& L, const LayerEpi& epi, bool in_u8, const void* in,
                               int64_t in_slot_stride, float* out, int64_t out_slot_stride, const dne_layer_desc* next,
-                              int n_slots, int sm_count, cudaStream_t st) {
+                              int n_slots, int sm_count, cudaStream_t st, float* xc) {
     S2dOut so;
+    so.xc = next ? nullptr : xc;
+    so.xc_kq = (L.hout * L.hout * L.cout) / 4;
     so.base = out;
     so.slot_stride = out_slot_stride;
     so.next_img = next ? 1 : 0;

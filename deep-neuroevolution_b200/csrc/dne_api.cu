@@ -4,6 +4,7 @@
 
 static thread_local char g_err[512] = "";
 unsigned long long g_dne_launches = 0;
+int g_dne_theta_tma = 1;     // TMA-fed shared-theta GEMM when a prepared region is current (dne_set_option("theta_tma", v))
 int g_dne_fuse_head = 1;     // combine + output head in one kernel (dne_set_option("fuse_head", v))
 
 void dne_set_error(const char* fmt, ...) {
@@ -46,6 +47,7 @@ extern "C" int dne_ctx_create(int device, dne_ctx** out) {
     c->ev_wait = c->ev_record = nullptr;
     c->ev_record_done = 0;
     c->ev_mode = 0;
+    for (int i = 0; i < DNE_MAX_PREP; ++i) c->prep[i].ws = nullptr, c->prep[i].theta = nullptr;
     cudaError_t e = cudaMalloc(&c->scratch, sizeof(double) * DNE_SCRATCH_DOUBLES);
     if (e != cudaSuccess) {
         delete c;
@@ -74,6 +76,9 @@ extern "C" int dne_set_option(const char* name, int value) {
     if (strcmp(name, "conv_tc") == 0 && value >= 0 && value <= 2) { g_dne_conv_tc = value; return DNE_OK; }
     if (strcmp(name, "gemv_bulk") == 0) { g_dne_gemv_bulk = value ? 1 : 0; return DNE_OK; }
     if (strcmp(name, "fuse_head") == 0) { g_dne_fuse_head = value ? 1 : 0; return DNE_OK; }
+    if (strcmp(name, "gemv_chunk_kb") == 0 && value >= 64 && value <= 4096) { extern int g_dne_gemv_chunk_kb; g_dne_gemv_chunk_kb = value; return DNE_OK; }
+    if (strcmp(name, "theta_mc") == 0) { extern int g_dne_theta_mc; g_dne_theta_mc = value ? 1 : 0; return DNE_OK; }
+    if (strcmp(name, "theta_tma") == 0) { g_dne_theta_tma = value ? 1 : 0; return DNE_OK; }
     if (strcmp(name, "gemv_stages") == 0 && value >= 2 && value <= 8) { extern int g_dne_gemv_stages; g_dne_gemv_stages = value; return DNE_OK; }
     if (strcmp(name, "gemv_prefetch") == 0 && value >= 0 && value <= 256) { extern int g_dne_gemv_prefetch; g_dne_gemv_prefetch = value; return DNE_OK; }
     if (strcmp(name, "gemv_ctas_per_sm") == 0 && value >= 1 && value <= 2) { g_dne_gemv_ctas_per_sm = value; return DNE_OK; }
@@ -92,6 +97,10 @@ extern "C" long long dne_launch_count(int reset) {
 // `capacity` launches.  on = 0 stops recording; the samples stay readable.
 extern "C" int dne_profile_enable(dne_ctx* ctx, int on, int capacity) {
     DNE_CHECK_ARG(ctx, "ctx is null");
+    if (on == 2) {                                  // resume after a pause (on = 0): keeps the samples taken so far
+        ctx->prof_on = ctx->ev ? 1 : 0;
+        return DNE_OK;
+    }
     if (on) {
         if (capacity < 1) capacity = 4096;
         if (capacity > ctx->ev_cap) {
@@ -143,8 +152,16 @@ struct ForwardPlan {
     int64_t act_elems[DNE_MAX_LAYERS];     // per slot
     DensePlan dense[DNE_MAX_LAYERS];
     size_t part_theta_off, part_noise_off;
+    size_t xc_off[DNE_MAX_LAYERS], wc_off[DNE_MAX_LAYERS];   // TMA-fed theta GEMM operands of dense layer l (0 = none)
     size_t total;
 };
+
+// dense layer l can take the TMA-fed theta GEMM: it directly follows a shifted-window conv layer (whose epilogue writes Xc)
+static bool tgm_candidate(const dne_net_desc* net, int l, const DensePlan& dp) {
+    if (l == 0 || net->layers[l].kind != DNE_DENSE || net->layers[l - 1].kind != DNE_CONV || !dp.decomposed) return false;
+    if (!dne_s2d_supported(net->layers[l - 1], l - 1 == 0)) return false;
+    return dne_tgm_supported(net->layers[l].cin, net->layers[l].cout, dp.k_per_split);
+}
 
 static int64_t layer_out_elems(const dne_layer_desc& L) {
     return L.kind == DNE_CONV ? (int64_t)L.hout * L.hout * L.cout : (int64_t)L.cout;
@@ -173,6 +190,16 @@ static int plan_forward(const dne_net_desc* net, int n_slots, int paired, bool s
             if (fp->dense[l].part_theta_floats > pt) pt = fp->dense[l].part_theta_floats;
             if (fp->dense[l].part_noise_floats > pn) pn = fp->dense[l].part_noise_floats;
         }
+    }
+    // operands of the TMA-fed theta GEMM: placed BEFORE the partial buffers so that their offsets do not depend on
+    // (paired, shared_theta) -- dne_theta_prepare and every later forward call on the workspace must agree on them
+    for (int l = 0; l < net->n_layers; ++l) {
+        fp->xc_off[l] = fp->wc_off[l] = 0;
+        if (!tgm_candidate(net, l, fp->dense[l])) continue;
+        fp->xc_off[l] = off;
+        off += align_up(dne_tgm_xc_bytes(n_slots, net->layers[l].cin), 256);
+        fp->wc_off[l] = off;
+        off += align_up(dne_tgm_wc_bytes(net->layers[l].cin, net->layers[l].cout), 256);
     }
     fp->part_theta_off = off;
     off += align_up(pt * sizeof(float), 256);
@@ -209,6 +236,53 @@ static LayerEpi make_layer_epi(const dne_layer_desc& L, const dne_net_desc* net,
     return epi;
 }
 
+// ---- prepared theta (TMA-fed theta GEMM) ---------------------------------------------------------------------------------
+void dne_prep_invalidate_theta(dne_ctx* ctx, const float* d_theta) {
+    for (int i = 0; i < DNE_MAX_PREP; ++i)
+        if (ctx->prep[i].theta == d_theta) ctx->prep[i].ws = nullptr, ctx->prep[i].theta = nullptr;
+}
+static bool prep_current(const dne_ctx* ctx, const void* ws, const float* d_theta, int n_slots) {
+    for (int i = 0; i < DNE_MAX_PREP; ++i)
+        if (ctx->prep[i].ws == ws && ctx->prep[i].theta == d_theta && ctx->prep[i].n_slots == n_slots) return true;
+    return false;
+}
+
+// Relays out the shared-theta weight matrices of the net's dense layers into the workspace (theta_prep_kernel) for the
+// TMA-fed theta GEMM, and remembers (workspace, theta) as current.  Call again whenever theta changes by any means other
+// than dne_adam_step / dne_sgd_step on the same context (those invalidate the entry themselves).  Forward calls on a
+// workspace without a current entry use the thread-staged GEMM: always correct, ~20 us slower per 256-slot tick.
+extern "C" int dne_theta_prepare(dne_ctx* ctx, const dne_net_desc* net, const float* d_theta, int n_slots, void* d_ws,
+                                 size_t ws_bytes, void* stream) {
+    DNE_CHECK_ARG(ctx && net && d_theta && d_ws && n_slots > 0, "bad arguments");
+    DNE_CHECK_ARG(((uintptr_t)d_ws & 255) == 0 && ((uintptr_t)d_theta & 15) == 0, "workspace / theta alignment");
+    ForwardPlan fp;
+    int rc = plan_forward(net, n_slots, 1, true, &fp);        // the prepared region's offsets do not depend on `paired`
+    if (rc) return rc;
+    if (ws_bytes < fp.total) {
+        dne_set_error("dne_theta_prepare: workspace too small (%zu < %zu)", ws_bytes, fp.total);
+        return DNE_ERR_WS;
+    }
+    for (int i = 0; i < DNE_MAX_PREP; ++i)                     // drop stale entries of this workspace
+        if (ctx->prep[i].ws == d_ws) ctx->prep[i].ws = nullptr, ctx->prep[i].theta = nullptr;
+    bool any = false;
+    for (int l = 0; l < net->n_layers; ++l) {
+        if (!fp.wc_off[l]) continue;
+        const dne_layer_desc& L = net->layers[l];
+        dne_launch_theta_prep(d_theta + L.off_w, L.cin, L.cout, (float*)((char*)d_ws + fp.wc_off[l]), (cudaStream_t)stream);
+        DNE_LAUNCH_CHECK();
+        any = true;
+    }
+    if (any) {
+        int slot = 0;
+        for (int i = 0; i < DNE_MAX_PREP; ++i)
+            if (!ctx->prep[i].ws) { slot = i; break; }
+        ctx->prep[slot].ws = d_ws;
+        ctx->prep[slot].theta = d_theta;
+        ctx->prep[slot].n_slots = n_slots;
+    }
+    return DNE_OK;
+}
+
 static int forward_impl(dne_ctx* ctx, const dne_net_desc* net, const float* d_theta, const int64_t* d_noise_idx,
                         const float* d_scale, const int32_t* d_theta_idx, const uint8_t* d_active, int n_slots,
                         int paired, const void* d_obs, const float* d_ob_mean, const float* d_ob_std,
@@ -242,6 +316,8 @@ static int forward_impl(dne_ctx* ctx, const dne_net_desc* net, const float* d_th
     bool use_s2d = (g_dne_conv_tc >= 2) && net->ob_kind == DNE_OB_ATARI_U8;
     for (int l = 0; l < net->n_layers && use_s2d; ++l)
         if (net->layers[l].kind == DNE_CONV) use_s2d = dne_s2d_supported(net->layers[l], l == 0);
+    // TMA-fed theta GEMM: only with a current prepared-theta region in THIS workspace for THIS theta (dne_theta_prepare)
+    const bool use_tgm = use_s2d && g_dne_theta_tma && d_theta_idx == nullptr && prep_current(ctx, d_ws, d_theta, n_slots);
     cudaStream_t st = (cudaStream_t)stream;
     // phase events (dne_set_phase_events): consumed by this call
     if (ctx->ev_wait && ctx->ev_mode == 0) {
@@ -281,8 +357,9 @@ static int forward_impl(dne_ctx* ctx, const dne_net_desc* net, const float* d_th
         const LayerEpi epi = make_layer_epi(L, net, d_vbn);
         if (L.kind == DNE_CONV && use_s2d) {
             const dne_layer_desc* next = (!last && net->layers[l + 1].kind == DNE_CONV) ? &net->layers[l + 1] : nullptr;
+            float* xc = (use_tgm && !last && fp.xc_off[l + 1]) ? (float*)(ws + fp.xc_off[l + 1]) : nullptr;
             rc = dne_launch_conv_layer_s2d(sa, L, epi, cur_u8, cur, cur_stride, out, out_stride, next, n_slots,
-                                           ctx->sm_count, st);
+                                           ctx->sm_count, st, xc);
             if (rc) {
                 dne_set_error("forward: s2d conv layer %d launch failed (%d)", l, rc);
                 return rc;
@@ -309,9 +386,16 @@ static int forward_impl(dne_ctx* ctx, const dne_net_desc* net, const float* d_th
                 head.out_slot_stride = d_out ? net->n_out : fp.act_elems[l + 1];
                 head.actions = d_actions;
             }
+            TgmOperands tgm;
+            const bool tg = use_tgm && fp.xc_off[l] && fp.dense[l].Gt == 0;
+            if (tg) {
+                tgm.Xc = (const float*)(ws + fp.xc_off[l]);
+                tgm.Wc = (const float*)(ws + fp.wc_off[l]);
+            }
             rc = dne_launch_dense_layer(ctx, sa, L, epi, fp.dense[l], (const float*)cur, cur_stride, out, out_stride,
                                         last ? d_actions : nullptr, (float*)(ws + fp.part_theta_off),
-                                        (float*)(ws + fp.part_noise_off), n_slots, st, fuse ? &head : nullptr);
+                                        (float*)(ws + fp.part_noise_off), n_slots, st, fuse ? &head : nullptr,
+                                        tg ? &tgm : nullptr);
             if (rc == 0 && fuse) {
                 DNE_LAUNCH_CHECK();
                 break;                                           // the head layer is done

@@ -67,10 +67,21 @@ struct DenseHead {
     int32_t* actions;          // nullable
 };
 bool dne_head_fusable(const dne_layer_desc& L, const DensePlan& p, const dne_layer_desc& head, const DensePlan& hp);
+// TMA-fed shared-theta GEMM (theta_gemm_tma.cu): both operands pre-arranged in the UMMA canonical layout, split hi / lo
+struct TgmOperands {
+    const float* Xc;           // [m tile][k quad][hi|lo][128][4], written by the producing conv epilogue
+    const float* Wc;           // [n tile][k quad][hi|lo][128][4], written by dne_theta_prepare
+};
+size_t dne_tgm_xc_bytes(int n_slots, int K);
+size_t dne_tgm_wc_bytes(int K, int N);
+bool dne_tgm_supported(int K, int N, int k_per_split);
+int dne_launch_theta_prep(const float* W, int K, int N, float* Wc, cudaStream_t st);
+int dne_launch_theta_gemm_tma(const float* Xc, const float* Wc, int M, int K, int N, int k_per_split, int n_split, float* part,
+                              cudaStream_t st);
 int dne_launch_dense_layer(const dne_ctx* ctx, const SlotArgs& sa, const dne_layer_desc& L, const LayerEpi& epi,
                            const DensePlan& p, const float* X, int64_t x_slot_stride, float* out,
                            int64_t out_slot_stride, int32_t* actions, float* part_theta, float* part_noise,
-                           int n_slots, cudaStream_t st, const DenseHead* head = nullptr);
+                           int n_slots, cudaStream_t st, const DenseHead* head = nullptr, const TgmOperands* tgm = nullptr);
 
 void dne_launch_ob_norm(const float* obs, const float* mean, const float* stdv, int64_t total, int dim, float* out,
                         cudaStream_t st);
@@ -83,4 +94,4 @@ bool dne_s2d_supported(const dne_layer_desc& L, bool in_u8);
 size_t dne_s2d_image_bytes(const dne_layer_desc& L);
 int dne_launch_conv_layer_s2d(const SlotArgs& sa, const dne_layer_desc& L, const LayerEpi& epi, bool in_u8, const void* in,
                               int64_t in_slot_stride, float* out, int64_t out_slot_stride, const dne_layer_desc* next,
-                              int n_slots, int sm_count, cudaStream_t st);
+                              int n_slots, int sm_count, cudaStream_t st, float* xc = nullptr);

@@ -636,9 +636,12 @@ int dne_launch_conv_layer_simt(const SlotArgs& sa, const dne_layer_desc& L, cons
 }
 
 // ---- dense-layer planning (shared by the ws query and the launcher) -----------------------------------
+int g_dne_gemv_chunk_kb = 1024;    // dne_set_option("gemv_chunk_kb", v): bytes of weights per GEMV work item (and per partial)
 static int pick_rows_per_chunk(int K, int N) {
-    // target ~512 KB of noise per work item (persistent bulk-copy GEMV), prefer exact divisors of K
-    int target = (int)((512 * 1024) / ((size_t)N * 4));
+    // target ~1 MB of noise per work item (persistent bulk-copy GEMV; r02 A/B: same GEMV time as 512 KB, half the partials
+    // for the combine kernel to read), prefer exact divisors of K
+    int target = (int)(((size_t)g_dne_gemv_chunk_kb * 1024) / ((size_t)N * 4));
+    if (target > 512) target = 512;           // GB_MAX_ROWS of gemv_bulk.cu (x staging buffer)
     if (target < 8) target = 8;
     if (target >= K) return K;
     for (int r = target; r >= target / 2 && r >= 1; --r)
@@ -688,7 +691,7 @@ bool dne_head_fusable(const dne_layer_desc& L, const DensePlan& p, const dne_lay
 int dne_launch_dense_layer(const dne_ctx* ctx, const SlotArgs& sa, const dne_layer_desc& L, const LayerEpi& epi,
                            const DensePlan& p, const float* X, int64_t x_slot_stride, float* out,
                            int64_t out_slot_stride, int32_t* actions, float* part_theta, float* part_noise,
-                           int n_slots, cudaStream_t st, const DenseHead* head) {
+                           int n_slots, cudaStream_t st, const DenseHead* head, const TgmOperands* tgm) {
     const int K = L.cin, N = L.cout;
     if (!p.decomposed) {
         if (N > DS_MAXN) return DNE_ERR_UNSUP;
@@ -705,8 +708,10 @@ int dne_launch_dense_layer(const dne_ctx* ctx, const SlotArgs& sa, const dne_lay
         return sm1 > sm2 ? sm1 : sm2;
     };
     if (p.Gt == 0) {
-        // tensor cores (tcgen05, 3xTF32) when enabled, fp32 SIMT otherwise
-        if (!(g_dne_conv_tc && dne_launch_theta_gemm_tc(X, n_slots, K, N, sa.theta + L.off_w, p.k_per_split, p.n_split,
+        // TMA-fed tcgen05 GEMM when both operands are pre-arranged (dne_theta_prepare + conv_s2d epilogue); else
+        // thread-staged tensor cores (tcgen05, 3xTF32) when enabled, fp32 SIMT otherwise
+        if (tgm && dne_launch_theta_gemm_tma(tgm->Xc, tgm->Wc, n_slots, K, N, p.k_per_split, p.n_split, part_theta, st) == 0) {
+        } else if (!(g_dne_conv_tc && dne_launch_theta_gemm_tc(X, n_slots, K, N, sa.theta + L.off_w, p.k_per_split, p.n_split,
                                                         part_theta, st) == 0)) {
             dim3 grid((N + DG_BN - 1) / DG_BN, (n_slots + DG_BM - 1) / DG_BM, p.n_split);
             dense_theta_gemm_kernel<<<grid, DG_THREADS, 0, st>>>(X, n_slots, K, N, sa.theta + L.off_w, p.k_per_split,

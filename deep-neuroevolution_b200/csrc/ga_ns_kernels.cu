@@ -53,6 +53,7 @@ __global__ void read_seed0_kernel(const int64_t* seeds, int64_t* out) { *out = s
 extern "C" int dne_ga_materialize(dne_ctx* ctx, const dne_net_desc* net, const int64_t* d_seeds,
                                   const float* d_powers, int len, const double* h_std, int mode, float* d_theta_out,
                                   void* stream) {
+    if (ctx) dne_prep_invalidate_theta(ctx, d_theta_out);
     DNE_CHECK_ARG(ctx && ctx->noise && net && d_seeds && d_theta_out && len >= 1, "bad arguments");
     DNE_CHECK_ARG(len == 1 || d_powers, "powers required for chains longer than 1");
     DNE_CHECK_ARG(mode == 0 || mode == 1, "mode must be 0 (gpu path) or 1 (cpu path)");
@@ -89,6 +90,7 @@ extern "C" int dne_ga_materialize(dne_ctx* ctx, const dne_net_desc* net, const i
 
 extern "C" int dne_ga_mutate(dne_ctx* ctx, const float* d_parent, int64_t seed, float power, int64_t P,
                              float* d_theta_out, void* stream) {
+    if (ctx) dne_prep_invalidate_theta(ctx, d_theta_out);
     DNE_CHECK_ARG(ctx && ctx->noise && d_parent && d_theta_out && P > 0, "bad arguments");
     DNE_CHECK_ARG(seed >= 0 && seed + P <= ctx->noise_count, "seed out of range");
     ga_mutate_kernel<<<(unsigned)cdiv64(P, 256), 256, 0, (cudaStream_t)stream>>>(d_parent, ctx->noise + seed, power,
@@ -223,6 +225,39 @@ extern "C" int dne_knn_novelty(const uint8_t* d_bc, const int32_t* d_bc_len, int
     cudaStream_t st = (cudaStream_t)stream;
     double* dist = (double*)d_ws;
     knn_dist_kernel<<<dim3(A, q), KNN_THREADS, 0, st>>>(d_bc, d_bc_len, d_archive, d_archive_len, t_max, D, dist, A);
+    DNE_LAUNCH_CHECK1();
+    knn_select_kernel<<<q, KNN_THREADS, 0, st>>>(dist, A, k, d_novelty);
+    DNE_LAUNCH_CHECK1();
+    return DNE_OK;
+}
+
+// Vector behaviour characterisations (MujocoPolicy: final (x, y) position, or the x/y trajectory: policies.py:292-299):
+// float64 vectors of equal length D, distance = plain L2 (nses.py:12-20 with n == m), float64 arithmetic in index order.
+__global__ void knn_dist_vec_kernel(const double* __restrict__ bc, const double* __restrict__ ar, int q, int A, int D,
+                                    double* __restrict__ dist) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (int64_t)q * A) return;
+    const int qi = (int)(i / A), ai = (int)(i % A);
+    double s = 0.0;
+    for (int d = 0; d < D; ++d) {
+        const double t = __dsub_rn(bc[(int64_t)qi * D + d], ar[(int64_t)ai * D + d]);
+        s = __dadd_rn(s, __dmul_rn(t, t));
+    }
+    dist[i] = sqrt(s);
+}
+
+extern "C" int dne_knn_novelty_vec(const double* d_bc, int q, const double* d_archive, int A, int D, int k, float* d_novelty,
+                                   void* d_ws, size_t ws_bytes, void* stream) {
+    DNE_CHECK_ARG(d_bc && d_archive && d_novelty && d_ws, "null pointer");
+    DNE_CHECK_ARG(q >= 1 && A >= 1 && D >= 1 && k >= 1, "bad sizes");
+    if (ws_bytes < (size_t)q * A * sizeof(double)) {
+        dne_set_error("dne_knn_novelty_vec: workspace too small");
+        return DNE_ERR_WS;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    double* dist = (double*)d_ws;
+    const int64_t n = (int64_t)q * A;
+    knn_dist_vec_kernel<<<(unsigned)cdiv64(n, 256), 256, 0, st>>>(d_bc, d_archive, q, A, D, dist);
     DNE_LAUNCH_CHECK1();
     knn_select_kernel<<<q, KNN_THREADS, 0, st>>>(dist, A, k, d_novelty);
     DNE_LAUNCH_CHECK1();

@@ -231,6 +231,7 @@ static int opt_grid(const dne_ctx* ctx, int64_t P) {
 extern "C" int dne_adam_step(dne_ctx* ctx, float* d_theta, float* d_m, float* d_v, const float* d_g, int64_t P,
                              double l2coeff, double stepsize, double beta1, double beta2, double epsilon, int t,
                              float* d_update_ratio, void* stream) {
+    if (ctx) dne_prep_invalidate_theta(ctx, d_theta);
     DNE_CHECK_ARG(ctx && d_theta && d_m && d_v && d_g && P > 0 && t >= 1, "bad arguments");
     cudaStream_t st = (cudaStream_t)stream;
     // optimizers.py:46 in double (python floats), rounded to float32 where it meets the float32 array
@@ -249,6 +250,7 @@ extern "C" int dne_adam_step(dne_ctx* ctx, float* d_theta, float* d_m, float* d_
 
 extern "C" int dne_sgd_step(dne_ctx* ctx, float* d_theta, float* d_v, const float* d_g, int64_t P, double l2coeff,
                             double stepsize, double momentum, float* d_update_ratio, void* stream) {
+    if (ctx) dne_prep_invalidate_theta(ctx, d_theta);
     DNE_CHECK_ARG(ctx && d_theta && d_v && d_g && P > 0, "bad arguments");
     cudaStream_t st = (cudaStream_t)stream;
     const int grid = opt_grid(ctx, P);

@@ -51,6 +51,7 @@ _SIGS = {
     "dne_perturb_forward_mlp": [_P, C.POINTER(NetDesc), _P, _P, _P, _P, _P, C.c_int, C.c_int, _P, _P, _P, _P, _P,
                                 C.c_size_t, _P],
     "dne_ob_stat_accumulate": [_P, C.c_int, _P, C.c_int, _P, _P, _P],
+    "dne_theta_prepare": [_P, C.POINTER(NetDesc), _P, C.c_int, _P, C.c_size_t, _P],
     "dne_vbn_ws_bytes": [C.POINTER(NetDesc), C.c_int, C.c_int, C.POINTER(C.c_size_t)],
     "dne_vbn_reference_pass": [_P, C.POINTER(NetDesc), _P, _P, _P, _P, _P, C.c_int, _P, C.c_int, _P, _P,
                                C.c_size_t, _P],
@@ -71,6 +72,7 @@ _SIGS = {
     "dne_ga_mutate": [_P, _P, C.c_int64, C.c_float, C.c_int64, _P, _P],
     "dne_ga_truncate": [_P, C.c_int, C.c_int, _P, _P],
     "dne_knn_ws_bytes": [C.c_int, C.c_int, C.POINTER(C.c_size_t)],
+    "dne_knn_novelty_vec": [_P, C.c_int, _P, C.c_int, C.c_int, C.c_int, _P, _P, C.c_size_t, _P],
     "dne_knn_novelty": [_P, _P, C.c_int, _P, _P, C.c_int, C.c_int, C.c_int, C.c_int, _P, _P, C.c_size_t, _P],
 }
 EXPORTS = sorted(list(_SIGS) + ["dne_last_error", "dne_version", "dne_launch_count"])

@@ -73,6 +73,8 @@ class SlotForward:
         net, L = self.net, F.lib()
         assert theta.dim() in (1, 2) and theta.shape[-1] == net.num_params
         if net.ob_kind == F.OB_ATARI_U8:
+            if self.theta_idx is None:
+                self.prepare(theta, n)
             F.check(L.dne_perturb_forward_conv(
                 self.ctx.handle, C.byref(net.desc), F.ptr(theta, torch.float32), F.ptr(self.noise_idx),
                 F.ptr(self.scale), F.ptr(self.theta_idx), F.ptr(self.active), n, int(paired),
@@ -85,6 +87,18 @@ class SlotForward:
             F.ptr(obs, torch.float32), F.ptr(ob_mean), F.ptr(ob_std), F.ptr(self.logits),
             F.ptr(self.ws), self.ws.numel(), F.stream_ptr()))
         return self.logits
+
+    def prepare(self, theta: torch.Tensor, n_slots: Optional[int] = None):
+        """Once per theta: dne_theta_prepare (tensor-core operand layout of the fc weights in this table's workspace).
+        Keyed by (pointer, torch in-place version, engine epoch, slot count); ESUpdate.step and the other engine methods
+        that rewrite theta through the C ABI bump the epoch of the context."""
+        n = self.n_slots if n_slots is None else int(n_slots)
+        key = (theta.data_ptr(), theta._version, getattr(self.ctx, "theta_epoch", 0), n)
+        if key == getattr(self, "_prep_key", None):
+            return
+        F.check(F.lib().dne_theta_prepare(self.ctx.handle, C.byref(self.net.desc), F.ptr(theta, torch.float32), n,
+                                          F.ptr(self.ws), self.ws.numel(), F.stream_ptr()))
+        self._prep_key = key
 
     # -- per episode (ESAtariPolicy) -------------------------------------------------------------------------
     def vbn_reference_pass(self, theta: torch.Tensor, ref_batch: torch.Tensor, active: Optional[torch.Tensor] = None):
@@ -145,6 +159,7 @@ class ESUpdate:
         """optimizer.update(-g + l2coeff*theta) (es.py:298).  Returns the device scalar update ratio."""
         g = self.g if g is None else g
         self.t += 1
+        self.ctx.theta_epoch = getattr(self.ctx, "theta_epoch", 0) + 1        # theta is rewritten through the C ABI
         L = F.lib()
         if self.kind == "adam":
             a = self.args

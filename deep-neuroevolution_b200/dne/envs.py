@@ -114,6 +114,46 @@ class SyntheticAtariEnv(BatchEnv):
         return self.ram[np.asarray(slots, dtype=np.int64)].copy()
 
 
+class DeterministicAtariEnv(BatchEnv):
+    """Atari-shaped test environment whose episodes are a pure function of the ACTIONS: the observation after t steps is
+    frame ``t % R`` of one fixed seeded sequence, the reward is 10 when ``(7*action + t) % 11 == 0``, the episode length is
+    fixed, the RAM drifts with the actions.  An episode's return / length / behaviour characterisation therefore depend
+    only on the policy weights, not on which slot, wave or rank ran it: world-size-1 and world-size-N runs of a driver
+    must agree exactly (tests/test_gpu_multi.py)."""
+
+    def __init__(self, n_slots: int, num_actions: int = 18, episode_len: int = 6, seed: int = 0, frames: int = 8,
+                 pin: bool = True):
+        self.n_slots = int(n_slots)
+        self.observation_space = Box(0, 255, (84, 84, 4), dtype=np.uint8)
+        self.action_space = Discrete(num_actions)
+        g = torch.Generator().manual_seed(seed)
+        self.frames = torch.randint(0, 256, (frames, 84, 84, 4), dtype=torch.uint8, generator=g)
+        obs = torch.zeros(self.n_slots, 84, 84, 4, dtype=torch.uint8)
+        self.obs = obs.pin_memory() if (pin and torch.cuda.is_available()) else obs
+        self.max_episode_steps = int(episode_len)
+        self.t = np.zeros(self.n_slots, dtype=np.int64)
+        self.ram = np.zeros((self.n_slots, 128), dtype=np.uint8)
+
+    def reset(self, slots):
+        slots = np.asarray(slots, dtype=np.int64)
+        self.t[slots] = 0
+        self.ram[slots] = 0
+        self.obs[torch.from_numpy(slots)] = self.frames[0]
+
+    def step(self, slots, actions):
+        slots = np.asarray(slots, dtype=np.int64)
+        a = np.asarray(actions).astype(np.int64)
+        t = self.t[slots]
+        rew = (((7 * a + t) % 11) == 0).astype(np.float32) * np.float32(10.0)
+        self.ram[slots, t % 128] = (a * 13 + t + 1) & 255
+        self.t[slots] = t + 1
+        self.obs[torch.from_numpy(slots)] = self.frames[torch.from_numpy((t + 1) % len(self.frames))]
+        return rew, self.t[slots] >= self.max_episode_steps
+
+    def get_ram(self, slots):
+        return self.ram[np.asarray(slots, dtype=np.int64)].copy()
+
+
 class SyntheticVectorEnv(BatchEnv):
     """Humanoid-shaped stub: float32 observations ~ N(0,1) of dimension ``ob_dim``,
     continuous actions of dimension ``ac_dim``, reward = -|a|^2*1e-3 + 1 (alive bonus), fixed length."""

@@ -32,16 +32,23 @@ logger = logging.getLogger(__name__)
 
 
 class BCArchive:
-    """Archive of uint8 BC sequences in HBM, last-row padded to a common t_max, with true lengths."""
+    """Archive of behaviour characterisations in HBM.  ``kind='trace'``: uint8 RAM sequences [t, 128] (ES Atari,
+    policies.py:410,418), last-row padded to a common t_max, with true lengths.  ``kind='vector'``: float64 vectors of one
+    length (MujocoPolicy final (x, y) position, policies.py:292-299)."""
 
-    def __init__(self, device, D=128):
-        self.device, self.D = device, D
-        self.seqs = []                      # host copies (np.uint8 [t, D])
+    def __init__(self, device, D=128, kind="trace"):
+        self.device, self.D, self.kind = device, D, kind
+        self.seqs = []                      # host copies (np.uint8 [t, D] / np.float64 [D])
         self._dev = self._len = None
         self._tmax = 0
 
     def append(self, bc: np.ndarray):
-        self.seqs.append(np.ascontiguousarray(bc, dtype=np.uint8))
+        if self.kind == "vector":
+            bc = np.ascontiguousarray(bc, dtype=np.float64).reshape(-1)
+            self.D = bc.size
+            self.seqs.append(bc)
+        else:
+            self.seqs.append(np.ascontiguousarray(bc, dtype=np.uint8))
         self._dev = None
 
     def __len__(self):
@@ -66,6 +73,20 @@ class BCArchive:
 def compute_novelty_vs_archive(archive: BCArchive, bcs, k: int) -> np.ndarray:
     """nses.py:22-32 for a batch of BC sequences (device k-NN)."""
     dev = archive.device
+    if len(bcs) == 0:                       # a rank whose shard of the population is empty (n_pairs < world)
+        return np.zeros(0, dtype=np.float32)
+    if archive.kind == "vector":
+        q, A, D = len(bcs), len(archive), archive.D
+        d_bc = torch.from_numpy(np.stack([np.asarray(b, dtype=np.float64).reshape(-1) for b in bcs])).to(dev)
+        if archive._dev is None:
+            archive._dev = torch.from_numpy(np.stack(archive.seqs)).to(dev)
+        nb = C.c_size_t()
+        F.check(F.lib().dne_knn_ws_bytes(q, A, C.byref(nb)))
+        ws = torch.empty(max(nb.value, 256), dtype=torch.uint8, device=dev)
+        nov = torch.empty(q, dtype=torch.float32, device=dev)
+        F.check(F.lib().dne_knn_novelty_vec(F.ptr(d_bc), q, F.ptr(archive._dev), A, D, int(k), F.ptr(nov), F.ptr(ws),
+                                            ws.numel(), F.stream_ptr()))
+        return nov.cpu().numpy()
     t_max = max(max(len(b) for b in bcs), max(len(s) for s in archive.seqs))
     d_arch, d_alen = archive.device_view(t_max)
     q = len(bcs)
@@ -90,7 +111,7 @@ def run_master(master_redis_cfg, log_dir, exp, *, max_iterations=None, n_slots=2
     # archive and the ranks all_gather (returns, lengths, novelty) -- a few floats per pair instead of the BC traces --
     # then the ES collectives (partial gradient with the global denominator, one all_reduce).  Everything that feeds the
     # archive or the parent choice comes from rank 0 (broadcast), so the replicas cannot drift apart.
-    # world == 1 executes exactly the single-GPU statements.  NOTE: the world > 1 path has not yet been run on >1 GPU.
+    # world == 1 executes exactly the single-GPU statements; tests/test_gpu_multi.py runs world 2 against world 1 on NCCL.
     if rank == 0:
         tlogger.start(log_dir)
     else:
@@ -113,10 +134,23 @@ def run_master(master_redis_cfg, log_dir, exp, *, max_iterations=None, n_slots=2
         policy.set_ref_batch(get_ref_batch(env, batch_size=128, rs=np.random.RandomState(seed)))
     runner = RolloutRunner(ctx, policy.net, env, n_slots=n_slots, group=2, pipeline=2 if n_slots % 4 == 0 else 1,
                            ref_batch=policy.ref_batch)
-    archive = BCArchive(dev)
+    # behaviour characterisation per policy family: RAM trace for the Atari policies (policies.py:410,418), final (x, y)
+    # position for MujocoPolicy (policies.py:292-299, bc_choice default)
+    vector_bc = policy.net.ob_kind == F.OB_VECTOR
+    bc_mode = "final" if vector_bc else "trace"
+    archive = BCArchive(dev, kind="vector" if vector_bc else "trace")
+    ob_stat = RunningStat(env.observation_space.shape, eps=1e-2) if policy.needs_ob_stat else None      # nses.py:72-75
+    ob_count_this_batch = 0
+
+    def ob_norm():
+        if ob_stat is None:
+            return None, None
+        policy.set_ob_stat(ob_stat.mean, ob_stat.std)
+        return policy.ob_mean, policy.ob_std
 
     def mean_bc(theta):                                    # nses.py:34-39 (one noiseless rollout)
-        res = runner.run(theta, [Unit(0, (0.0, 0.0))], tslimit_max, collect_bc="trace")
+        om, osd = ob_norm()
+        res = runner.run(theta, [Unit(0, (0.0, 0.0), noiseless=True)], tslimit_max, collect_bc=bc_mode, ob_mean=om, ob_std=osd)
         return res.bcs[0][0]
 
     theta_dict, optimizer_dict = {}, {}
@@ -141,7 +175,21 @@ def run_master(master_redis_cfg, log_dir, exp, *, max_iterations=None, n_slots=2
         sig = np.float32(config.noise_stdev)
         units = [Unit(int(i), (sig, -sig)) for i in idx]
         lo, hi = shard.shard_bounds(n_pairs, rank, world)
-        res = runner.run(optimizer.device_theta, units[lo:hi], tslimit, collect_bc="trace")
+        om, osd = ob_norm()
+        res = runner.run(optimizer.device_theta, units[lo:hi], tslimit, collect_bc=bc_mode, ob_mean=om, ob_std=osd,
+                         ac_noise_std=getattr(policy, "ac_noise_std", 0.0),
+                         random_stream=np.random.RandomState((seed + 1000 * it + rank) % (2 ** 31)),
+                         save_obs_prob=config.calc_obstat_prob if ob_stat is not None else 0.0)
+        if ob_stat is not None and config.calc_obstat_prob != 0:                                         # nses.py:196-199
+            t = torch.from_numpy(np.concatenate([res.ob_sum, res.ob_sumsq, [float(res.ob_count)]])).to(dev)
+            shard.all_reduce_sum_(t)
+            tot = t.cpu().numpy()
+            Dd = (len(tot) - 1) // 2
+            ob_count_this_batch = int(round(tot[-1]))
+            if ob_count_this_batch > 0:
+                shp = ob_stat.sum.shape
+                ob_stat.increment(tot[:Dd].astype(np.float32).reshape(shp), tot[Dd:2 * Dd].astype(np.float32).reshape(shp),
+                                  ob_count_this_batch)
         bcs = [res.bcs[u][g] for u in range(hi - lo) for g in range(2)]
         novelty_n2 = compute_novelty_vs_archive(archive, bcs, k).reshape(hi - lo, 2).astype(np.float32)   # nses.py:381-384
         returns_n2, lengths_n2 = res.returns, res.lengths

@@ -95,6 +95,9 @@ long long   dne_launch_count(int reset);
  *   "conv_tc" = 1 (default): member convolutions + the shared-theta GEMM on the tensor cores (tcgen05.mma kind::tf32,
  *               3xTF32 split, TMEM accumulators); 0 selects the fp32 SIMT kernels (kept for A/B parity checks).
  *   "gemv_bulk" = 1 (default): noise GEMV through the cp.async.bulk shared-memory ring; 0 = plain-LDG kernel.
+ *   "conv_tc" = 2 (default): shifted-window convolutions with TMA-fed images / weights (conv_s2d.cu); 1: im2col-staged tcgen05
+ *               convolutions (tc_conv.cu); 0: fp32 SIMT.  "theta_tma" = 1 (default): TMA-fed shared-theta GEMM when prepared.
+ *               "fuse_head" = 1 (default): combine + output head + argmax in one kernel.
  *   "gemv_ctas_per_sm" = 1|2 (default 2), "gemv_stages" = 2..8 (default 6): persistent-grid size / ring depth of it.
  *   "gemv_prefetch" = 0..256 (default 0): L2 prefetch distance in 16 KB stages (measured slower on B200; off). */
 int         dne_set_option(const char* name, int value);
@@ -126,6 +129,15 @@ int dne_perturb_forward_conv(dne_ctx* ctx, const dne_net_desc* net, const float*
                              const uint8_t* d_obs, const float* d_vbn,
                              int32_t* d_actions, float* d_logits,
                              void* d_ws, size_t ws_bytes, void* stream);
+
+/* Optional, once per generation: relays out the shared weight matrices of the net's large dense layers
+ * (theta_w[K, N] of the fc layer: the x . theta_w half of x . (theta_w + s*noise), policies.py:327 / dqn.py:46) into the
+ * workspace in the tensor-core operand layout (TF32 hi / lo planes), so that the following dne_perturb_forward_conv calls
+ * on the SAME (d_ws, d_theta, n_slots) feed that GEMM by TMA instead of staging it through threads.  The entry stays
+ * current until dne_adam_step / dne_sgd_step on this context rewrite d_theta (they drop it themselves); after any OTHER
+ * write to d_theta call it again.  Without a current entry the forward is still correct (thread-staged GEMM). */
+int dne_theta_prepare(dne_ctx* ctx, const dne_net_desc* net, const float* d_theta, int n_slots, void* d_ws, size_t ws_bytes,
+                      void* stream);
 
 /* Phase-shifted double buffering of two slot tables on two CUDA streams: the NEXT dne_perturb_forward_* call on ctx
  * makes its stream wait for wait_event (cudaEvent_t, nullable) before its first kernel and records record_event
@@ -221,6 +233,11 @@ int dne_knn_ws_bytes(int q, int A, size_t* out_bytes);
 int dne_knn_novelty(const uint8_t* d_bc, const int32_t* d_bc_len, int q,
                     const uint8_t* d_archive, const int32_t* d_archive_len, int A,
                     int t_max, int D, int k, float* d_novelty, void* d_ws, size_t ws_bytes, void* stream);
+
+/* Same for vector BCs (MujocoPolicy: final (x, y) position / trajectory, policies.py:292-299): float64 [*, D] of equal
+ * length, plain L2 distance in float64 (nses.py:12-20 with equal lengths), mean of the k smallest. */
+int dne_knn_novelty_vec(const double* d_bc, int q, const double* d_archive, int A, int D, int k, float* d_novelty,
+                        void* d_ws, size_t ws_bytes, void* stream);
 
 #ifdef __cplusplus
 }

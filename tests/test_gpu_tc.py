@@ -241,3 +241,59 @@ def test_tcgen05_shifted_window_operand(C_, pixp, W, taps, N, row0, use_tma):
         ref[ok] += flat[rows[ok]].astype(np.float64) @ Bw[:, t * C_:(t + 1) * C_].astype(np.float64).T
     assert valid.sum() >= 32
     np.testing.assert_array_equal(got[valid], ref[valid].astype(np.float32))
+
+
+def test_theta_gemm_tma_vs_thread_staged_and_invalidation(ctx, host_noise):
+    """The TMA-fed shared-theta GEMM (dne_theta_prepare + Xc written by the conv3 epilogue) against the thread-staged GEMM
+    on 256 and 128 slots, and the staleness rule: after dne_adam_step rewrote theta through the same context the prepared
+    entry is dropped, so the next forward must see the NEW weights (with and without a fresh prepare)."""
+    from dne.engine import ESUpdate
+    net, net_o = N.make_net("LargeModel"), O.make_net("LargeModel")
+    P = net.num_params
+    rs = np.random.RandomState(123)
+    theta0 = (rs.randn(P) * 0.05).astype(np.float32)
+    L = F.lib()
+    for n_slots in (256, 128, 6):
+        pidx = rs.randint(0, NOISE_COUNT - P + 1, size=n_slots // 2).astype(np.int64)
+        idx, scale = np.repeat(pidx, 2), np.tile([0.005, -0.005], n_slots // 2).astype(np.float32)
+        obs = cuda(rs.randint(0, 256, size=(n_slots, 84, 84, 4)).astype(np.uint8))
+        d_theta = cuda(theta0)
+        out = {}
+        try:
+            for tma in (1, 0):
+                F.check(L.dne_set_option(b"theta_tma", tma))
+                sf = SlotForward(ctx, net, n_slots)
+                sf.set_slots(idx, scale)
+                a = sf.forward(d_theta, obs, paired=True).cpu().numpy()
+                out[tma] = (sf.logits.cpu().numpy(), a)
+        finally:
+            F.check(L.dne_set_option(b"theta_tma", 1))
+        bound = 2e-5 * np.maximum(1.0, np.abs(out[0][0]).max(axis=1))
+        assert (np.abs(out[1][0] - out[0][0]).max(axis=1) <= bound).all(), n_slots
+    # staleness: one Adam step through the same context, then forward again on the same workspace
+    upd = ESUpdate(ctx, theta0, "adam", stepsize=0.05)
+    n_slots = 128
+    pidx = rs.randint(0, NOISE_COUNT - P + 1, size=n_slots // 2).astype(np.int64)
+    idx, scale = np.repeat(pidx, 2), np.tile([0.005, -0.005], n_slots // 2).astype(np.float32)
+    obs_h = rs.randint(0, 256, size=(n_slots, 84, 84, 4)).astype(np.uint8)
+    obs = cuda(obs_h)
+    sf = SlotForward(ctx, net, n_slots)
+    sf.set_slots(idx, scale)
+    sf.forward(upd.theta, obs, paired=True)
+    before = sf.logits.clone()
+    upd.step(0.005, cuda((rs.randn(P)).astype(np.float32)))                 # theta rewritten in place (same pointer)
+    # raw C-ABI forward WITHOUT a new prepare: must not use the stale operand (falls back to the thread-staged GEMM)
+    F.check(L.dne_perturb_forward_conv(ctx.handle, C.byref(net.desc), F.ptr(upd.theta), F.ptr(sf.noise_idx), F.ptr(sf.scale),
+                                       None, None, n_slots, 1, F.ptr(obs), None, F.ptr(sf.actions), F.ptr(sf.logits),
+                                       F.ptr(sf.ws), sf.ws.numel(), F.stream_ptr()))
+    raw = sf.logits.cpu().numpy()
+    sf.forward(upd.theta, obs, paired=True)                                   # engine path: re-prepares (epoch changed)
+    eng = sf.logits.cpu().numpy()
+    th = upd.theta.cpu().numpy()
+    rows = [0, 1, 64, 127]
+    ref = np.stack([O.forward(net_o, (th + np.float32(scale[s]) * host_noise[idx[s]:idx[s] + P]).astype(np.float32),
+                              obs_h[s:s + 1])[0][0] for s in rows])
+    bound = 2e-5 * np.maximum(1.0, np.abs(ref).max(axis=1))
+    assert (np.abs(raw[rows] - ref).max(axis=1) <= bound).all()
+    assert (np.abs(eng[rows] - ref).max(axis=1) <= bound).all()
+    assert float((before - torch.from_numpy(eng).to(DEV)).abs().max()) > 1e-3       # the step really changed the outputs

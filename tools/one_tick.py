@@ -10,6 +10,9 @@ name = os.environ.get("NET", "LargeModel"); slots = int(os.environ.get("SLOTS", 
 count = int(os.environ.get("NOISE_COUNT", 60_000_000))
 host = np.random.RandomState(123).randn(count).astype(np.float32)
 ctx = make_context(0, SharedNoiseTable(host_noise=host, device="cuda:0"))
+from dne import _ffi as F
+for kv in filter(None, os.environ.get("DNE_OPTS", "").split(",")):
+    k, v = kv.split("="); F.check(F.lib().dne_set_option(k.encode(), int(v)))
 net = nets.make_net(name); P = net.num_params
 rs = np.random.RandomState(0)
 theta = torch.from_numpy((rs.randn(P) * 0.05).astype(np.float32)).cuda()
