@@ -8,27 +8,32 @@
 // What changed against conv_tc_kernel (r01: 126 us per 256-slot tick, tensor pipe 13-18 %):
 //   * NO im2col copy.  The (zero padded) input is space-to-depth'ed by the stride S, which turns the KSxKS/stride-S
 //     convolution into a (KS/S)x(KS/S)/stride-1 convolution over a W x W pixel grid with S*S*CIN channels.  The image
-//     is kept in shared memory as channel-quad planes  img[plane][pixel][4]  -- which IS the UMMA K-major no-swizzle
+//     is kept in shared memory as channel-octet planes  img[plane][pixel][8 x fp16]  -- which IS the UMMA K-major no-swizzle
 //     canonical layout of a matrix whose rows are the pixels (8 pixels = one 128-byte core matrix, SBO = 128, next
-//     channel quad LBO = PIXP*16 bytes).  Output position m = oy*W + ox reads pixel m + ty*W + tx for tap (ty, tx): the
+//     channel octet LBO = PIXP*16 bytes; a 16-byte row holds 8 fp16 channels).  Output position m = oy*W + ox reads pixel m + ty*W + tx for tap (ty, tx): the
 //     SAME image at a start address shifted by (ty*W+tx)*16 bytes.  One smem descriptor per (tap, channel octet, M tile);
 //     rows with ox >= HOUT are junk accumulator rows that the epilogue skips (dev/tc_window.cu is the hardware
 //     self-test of this addressing; tests/test_gpu_tc.py::test_tcgen05_shifted_window_operand).
 //     Staging traffic per member drops from KS*KS/(S*S) x the input (conv3: 9x) to 1x, and for every layer but the first
 //   * the image is not staged by threads at all: the PRODUCING layer's epilogue writes the next layer's image (already
-//     space-to-depth'ed, zero padded, split into TF32 hi / lo planes) to global memory in exactly the shared-memory
+//     space-to-depth'ed, zero padded, split into fp16 hi / lo planes) to global memory in exactly the shared-memory
 //     layout, and a producer thread brings it in with cp.async.bulk (TMA), one channel-octet group per mbarrier, so the
 //     MMAs of member i overlap the loads of member i+1 (a group's buffer is released by tcgen05.commit).
-//     The first layer converts the uint8 frame (exact in TF32: one plane, /255 applied to the accumulator).
+//     The first layer converts the uint8 frame (exact in fp16: one plane, /255 applied to the accumulator).
 //   * the member's raw weights are not fetched by the staging threads either (r02 first version: one serialized global
 //     round trip per 16 KB chunk, 35-47K cycles per member against 6-16K of MMA work): a second producer thread streams
 //     the chunk's theta rows and noise rows (16-byte aligned supersets of the arbitrarily aligned slices) with
 //     cp.async.bulk into the ring stage that will hold the operand tile, NSTB chunks deep; converter warps read the raw
 //     rows from shared memory, perturb + split, and overwrite the SAME stage with the canonical [B_hi ; B_lo] tile.
 //   * persistent CTAs (one per SM), three pipelines: A groups (TMA or staging warps <-> MMA), B ring (staging warps
-//     <-> MMA: the member's perturbed weights fl(theta + fl(s*noise)) split hi/lo, [B_hi; B_lo] stacked along N), and a
+//     <-> MMA: the member's perturbed weights fl(theta + fl(s*noise)) split h0/h1, [B_h0; B_h1] stacked along N), and a
 //     double-buffered TMEM accumulator (MMA <-> epilogue warps), so staging, MMA issue and epilogue of consecutive
-//     members overlap.  fp32 parity through 3xTF32: D = A_hi*[B_hi;B_lo] (one N = 2*COUT MMA) + A_lo*B_hi.
+//     members overlap.
+//   * arithmetic: tcgen05.mma kind::f16 on 2 x fp16 splits (tc05.cuh: x = h0 + h1*2^-11, 22 significand bits; uint8 pixels
+//     are exact in fp16 and need one plane) -- twice the MAC rate and half the operand bytes of the 3xTF32 formulation the
+//     first r02 version used (the kernels are MMA bound): main accumulator D0 = A_h0*B_h0, correction accumulator
+//     D1 = A_h0*B_h1 + A_h1*B_h0 (B_h0 and B_h1 stacked along N: one N = 2*COUT MMA + one N = COUT MMA per K = 16 step),
+//     result = D0 + 2^-11 * D1.  fp16 x fp16 products are exact in the fp32 accumulators.
 #include "common.cuh"
 #include "forward.cuh"
 #include "epilogue.cuh"
@@ -57,7 +62,7 @@ constexpr int S2D_EPI_THREADS = S2D_EPI_WARPS * 32;
 constexpr int S2D_THREADS = S2D_STAGE_THREADS + S2D_EPI_THREADS + 96;   // + MMA warp + image producer warp + weight producer warp
 constexpr int S2D_FRAME_BYTES = 84 * 84 * 4;                            // the uint8 frame stack of the first layer
 constexpr int S2D_FRAME_STRIDE = (S2D_FRAME_BYTES + 127) / 128 * 128;
-constexpr int S2D_MAX_GROUPS = 16;
+constexpr int S2D_MAX_GROUPS = 8;
 constexpr int S2D_MAX_BST = 4;
 constexpr int S2D_SMEM_BUDGET = 226 * 1024;
 
@@ -71,17 +76,25 @@ struct S2dGeom {
 __host__ __device__ constexpr S2dGeom s2d_geom(int CIN, int KS, int S, int HIN, int HOUT, int PAD, bool in_u8) {
     S2dGeom g{};
     const int HP = (HOUT - 1) * S + KS;
-    g.S = S; g.PADB = PAD; g.W = HP / S; g.KT = KS / S; g.CIN = CIN; g.CP = S * S * CIN; g.NG = g.CP / 8;
+    // plane = 8 channels (one 16-byte fp16 row per pixel); group = 16 channels = one K = 16 MMA step = 2 planes per part
+    g.S = S; g.PADB = PAD; g.W = HP / S; g.KT = KS / S; g.CIN = CIN; g.CP = S * S * CIN; g.NG = g.CP / 16;
     g.NPIX = g.W * g.W; g.PIXP = (g.NPIX + 7) / 8 * 8; g.PARTS = in_u8 ? 1 : 2; g.LBO = g.PIXP * 16;
     g.GROUP_BYTES = g.PARTS * 2 * g.LBO; g.IMG_BYTES = g.NG * g.GROUP_BYTES; g.HIN = HIN;
     return g;
+}
+
+constexpr int s2d_taps_per_chunk(int ntap, int piece_stride) {       // largest divisor of ntap whose raw landing zone fits ~26 KB
+    int best = 1;
+    for (int t = 1; t <= ntap; ++t)
+        if (ntap % t == 0 && 2 * t * piece_stride <= 26000) best = t;
+    return best;
 }
 
 template <int CIN, int COUT, int KS, int S, int HIN, int HOUT, int PAD, bool IN_U8>
 struct S2dCfg {
     static constexpr S2dGeom G = s2d_geom(CIN, KS, S, HIN, HOUT, PAD, IN_U8);
     static_assert(((HOUT - 1) * S + KS) % S == 0 && KS % S == 0, "space-to-depth needs S | KS and S | padded size");
-    static_assert(CIN % 4 == 0 && COUT % 16 == 0 && G.CP % 8 == 0 && G.NG <= S2D_MAX_GROUPS, "tile constraints");
+    static_assert(CIN % 4 == 0 && COUT % 16 == 0 && G.CP % 16 == 0 && G.NG <= S2D_MAX_GROUPS, "tile constraints");
     static constexpr int W = G.W, KT = G.KT, NTAP = KT * KT, NG = G.NG, PIXP = G.PIXP, LBO_A = G.LBO;
     static constexpr int PARTS = G.PARTS, GROUP_BYTES = G.GROUP_BYTES, IMG_BYTES = G.IMG_BYTES;
     static constexpr int MMAX = (HOUT - 1) * (W + 1);            // largest valid accumulator row
@@ -90,28 +103,31 @@ struct S2dCfg {
     static constexpr int REACH = MT * 128 + MAXOFF;              // pixels a descriptor may touch from a plane start
     static constexpr int SLACK = REACH > PIXP ? ((REACH - PIXP) * 16 + 127) / 128 * 128 : 0;
     static constexpr int A_REGION = IMG_BYTES + SLACK;
-    static constexpr int LBO_B = 2 * COUT * 16;                  // [B_hi ; B_lo] stacked along N
-    static constexpr int CHUNK_K = NTAP * 8;                     // k rows of one chunk: every tap of one channel octet
-    static constexpr int B_STAGE = (CHUNK_K / 4) * LBO_B;
-    // raw landing zone of a chunk inside its ring stage: NTAP pieces of 8 contiguous weight rows for theta, then for the
-    // noise; each piece is the 16-byte aligned superset of its rows (+16 bytes)
-    static constexpr int PIECE = 8 * COUT * 4;
+    static constexpr int LBO_B = 2 * COUT * 16;                  // [B_h0 ; B_h1] stacked along N, 8 fp16 k values per row
+    // raw landing zone of a chunk inside its ring stage: per tap one piece of 16 contiguous fp32 weight rows for theta and
+    // one for the noise; each piece is the 16-byte aligned superset of its rows (+16 bytes)
+    static constexpr int PIECE = 16 * COUT * 4;
     static constexpr int PIECE_STRIDE = PIECE + 16;
-    static constexpr int RAW_BYTES = 2 * NTAP * PIECE_STRIDE;
-    static constexpr int BST_BYTES = (cmax(B_STAGE, RAW_BYTES) + 127) / 128 * 128;
+    static constexpr int TPC = s2d_taps_per_chunk(NTAP, PIECE_STRIDE);   // taps per chunk
+    static constexpr int NCPG = NTAP / TPC;                      // chunks per channel group
+    static constexpr int NCH = NG * NCPG;                        // chunks per member
+    static constexpr int B_TILE = TPC * 2 * LBO_B;               // TPC taps x 16 k = TPC*2 k-octet planes
+    static constexpr int RAW_BYTES = 2 * TPC * PIECE_STRIDE;
+    static constexpr int BST_BYTES = (cmax(B_TILE, RAW_BYTES) + 127) / 128 * 128;
     static constexpr int FRAME_REGION = IN_U8 ? 2 * S2D_FRAME_STRIDE : 0;        // double-buffered raw uint8 frame
     static constexpr int NSTB = cmin(S2D_MAX_BST, (S2D_SMEM_BUDGET - A_REGION - FRAME_REGION - 256) / BST_BYTES);
     static_assert(NSTB >= 2, "shared memory: B ring too shallow");
     static constexpr int SMEM_BYTES = A_REGION + NSTB * BST_BYTES + FRAME_REGION + 256;
-    static constexpr int ACC_COLS = MT * 2 * COUT;               // one accumulator buffer
+    static constexpr int ACC_COLS = MT * 2 * COUT;               // one accumulator buffer: per M tile [main | correction]
     static constexpr int TMEM_COLS = 2 * ACC_COLS <= 32 ? 32 : 2 * ACC_COLS <= 64 ? 64 : 2 * ACC_COLS <= 128 ? 128 : 2 * ACC_COLS <= 256 ? 256 : 512;
     static_assert(2 * ACC_COLS <= 512, "TMEM: double-buffered accumulators do not fit");
-    static constexpr int B_UNITS = COUT * NTAP * 2;              // (column n, k quad) units per chunk
+    static constexpr int B_UNITS = COUT * TPC * 2;               // (column n, k octet) units per chunk
     // converter groups: chunk c is converted by group c % NGRP (independent streams hide the per-chunk hand-off latency)
-    static constexpr int NGRP = B_UNITS <= 512 ? 2 : 1;
+    static constexpr int NGRP = 2;
     static constexpr int WPG = S2D_STAGE_WARPS / NGRP, TG = 32 * WPG;
     static constexpr int B_UPT = (B_UNITS + TG - 1) / TG;
-    static_assert(TG % COUT == 0 && NG % NGRP == 0, "B unit map: a thread keeps its column; groups alternate chunks");
+    static_assert(TG % COUT == 0 && NCH % NGRP == 0, "B unit map: a thread keeps its column; groups alternate chunks");
+    static_assert(!IN_U8 || NCPG == 1, "the uint8 frame is staged per channel group by the group's (only) chunk");
 };
 
 // Where the epilogue writes: NHWC floats (feeding a dense layer) or the NEXT conv layer's image.
@@ -121,7 +137,7 @@ struct S2dOut {
     int next_img;               // 0: NHWC [HOUT*HOUT][COUT];  1: image of the next layer (geometry below)
     int nS, nPADB, nW, nPIXP, nHP;
     float* xc;                  // nullable (NHWC mode only): the same vector as the A operand of the TMA-fed theta GEMM,
-    int xc_kq;                  //   Xc[slot / 128][k quad][hi | lo][slot % 128][4]  (theta_gemm_tma.cu), xc_kq = K / 4
+    int xc_ko;                  //   Xc[slot / 128][k octet][h0 | h1][slot % 128][8 x fp16]  (theta_gemm_tma.cu), xc_ko = K / 8
 };
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -131,6 +147,7 @@ conv_s2d_kernel(SlotArgs sa, int64_t off_w, LayerEpi epi, const void* __restrict
                 S2dOut so, int n_slots) {
     using Cfg = S2dCfg<CIN, COUT, KS, S, HIN, HOUT, PAD, IN_U8>;
     constexpr int NG = Cfg::NG, NSTB = Cfg::NSTB, MT = Cfg::MT, NTAP = Cfg::NTAP, W = Cfg::W, KT = Cfg::KT;
+    constexpr int TPC = Cfg::TPC, NCPG = Cfg::NCPG, NCH = Cfg::NCH;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
     __shared__ uint64_t a_full[NG], a_empty[NG], raw_full[NSTB], b_full[NSTB], b_empty[NSTB], acc_full[2], acc_empty[2];
@@ -176,7 +193,7 @@ conv_s2d_kernel(SlotArgs sa, int64_t off_w, LayerEpi epi, const void* __restrict
 
     if (warp == S2D_STAGE_WARPS + S2D_EPI_WARPS) {
         // ================= MMA warp: converged loop, one elected lane issues (tc05.cuh: elect_one) =================
-        constexpr uint32_t IDESC2 = idesc_tf32(128, 2 * COUT), IDESC1 = idesc_tf32(128, COUT);
+        constexpr uint32_t IDESC2 = idesc_f16(128, 2 * COUT), IDESC1 = idesc_f16(128, COUT);
         const uint64_t dA0 = smem_desc(sA, Cfg::LBO_A, 128), dB0 = smem_desc(sB, Cfg::LBO_B, 128);
         uint32_t cb = 0, it = 0;
         for (int slot = blockIdx.x; slot < n_slots; slot += gridDim.x) {
@@ -185,34 +202,36 @@ conv_s2d_kernel(SlotArgs sa, int64_t off_w, LayerEpi epi, const void* __restrict
             mbar_wait(&acc_empty[buf], ((it >> 1) & 1) ^ 1);     // the epilogue has drained this accumulator buffer
             fence_after_thread_sync();
             const uint32_t d0 = tmem_base + buf * Cfg::ACC_COLS;
-            for (int g = 0; g < NG; ++g, ++cb) {
+            for (int c = 0; c < NCH; ++c, ++cb) {
+                const int g = c / NCPG, tc = c - g * NCPG;
                 const uint32_t st = cb % NSTB;
-                mbar_wait(&a_full[g], it & 1);
-                S2D_TR(lane == 0 && it < 2, S2D_EV(it, g, 4));
+                if (tc == 0) mbar_wait(&a_full[g], it & 1);
+                S2D_TR(lane == 0 && it < 2 && c < 16, S2D_EV(it, c, 4));
                 mbar_wait(&b_full[st], (cb / NSTB) & 1);
-                S2D_TR(lane == 0 && it < 2, S2D_EV(it, g, 5));
+                S2D_TR(lane == 0 && it < 2 && c < 16, S2D_EV(it, c, 5));
                 fence_after_thread_sync();
                 if (elect_one()) {
                     const uint64_t dAg = dA0 + (uint64_t)((g * Cfg::GROUP_BYTES) >> 4);
                     const uint64_t dBs = dB0 + (uint64_t)((st * Cfg::BST_BYTES) >> 4);
 #pragma unroll
-                    for (int tap = 0; tap < NTAP; ++tap) {
+                    for (int tl = 0; tl < TPC; ++tl) {
+                        const int tap = tc * TPC + tl;
                         const int toff = (tap / KT) * W + (tap % KT);
-                        const uint64_t dB = dBs + (uint64_t)((tap * 2 * Cfg::LBO_B) >> 4);
+                        const uint64_t dB = dBs + (uint64_t)((tl * 2 * Cfg::LBO_B) >> 4);
 #pragma unroll
                         for (int mt = 0; mt < MT; ++mt) {
                             const uint64_t dAh = dAg + (uint64_t)(mt * 128 + toff);         // 16-byte units == pixels
                             const uint32_t d = d0 + mt * 2 * COUT;
-                            mma_tf32(d, dAh, dB, IDESC2, (g | tap) != 0);                                     // A_hi * [B_hi ; B_lo]
-                            if (!IN_U8) mma_tf32(d, dAh + (uint64_t)((2 * Cfg::LBO_A) >> 4), dB, IDESC1, 1);   // A_lo * B_hi
+                            mma_f16(d, dAh, dB, IDESC2, (c | tl) != 0);                                       // A_h0 * [B_h0 ; B_h1]
+                            if (!IN_U8) mma_f16(d + COUT, dAh + (uint64_t)((2 * Cfg::LBO_A) >> 4), dB, IDESC1, 1);   // A_h1 * B_h0 -> correction
                         }
                     }
                     mma_commit(&b_empty[st]);
-                    mma_commit(&a_empty[g]);
-                    if (g == NG - 1) mma_commit(&acc_full[buf]);
+                    if (tc == NCPG - 1) mma_commit(&a_empty[g]);
+                    if (c == NCH - 1) mma_commit(&acc_full[buf]);
                 }
                 __syncwarp();
-                S2D_TR(lane == 0 && it < 2, S2D_EV(it, g, 6));
+                S2D_TR(lane == 0 && it < 2 && c < 16, S2D_EV(it, c, 6));
             }
             ++it;
         }
@@ -249,21 +268,23 @@ conv_s2d_kernel(SlotArgs sa, int64_t off_w, LayerEpi epi, const void* __restrict
                 const float* th = slot_theta(sa, slot) + off_w;
                 const float* nz = sa.noise + sa.noise_idx[slot] + off_w;
                 const int a_t = (int)(((uintptr_t)th >> 2) & 3), a_n = (int)(((uintptr_t)nz >> 2) & 3);
-                for (int g = 0; g < NG; ++g, ++cb) {
+                for (int c = 0; c < NCH; ++c, ++cb) {
+                    const int g = c / NCPG, tc = c - g * NCPG;
                     const uint32_t st = cb % NSTB;
                     mbar_wait(&b_empty[st], ((cb / NSTB) & 1) ^ 1);
-                    S2D_TR(cb < 2 * NG, S2D_EV(cb / NG, g, 0));
+                    S2D_TR(cb < 2 * NCH && c < 16, S2D_EV(cb / NCH, c, 0));
                     mbar_arrive_expect_tx(&raw_full[st], Cfg::RAW_BYTES);
                     uint8_t* dst = gB + st * Cfg::BST_BYTES;
-                    const int cp = 8 * g, pp = cp / CIN, ci = cp % CIN, py = pp / S, px = pp % S;
+                    const int cp = 16 * g, pp = cp / CIN, ci = cp % CIN, py = pp / S, px = pp % S;
 #pragma unroll
-                    for (int tap = 0; tap < NTAP; ++tap) {
+                    for (int tl = 0; tl < TPC; ++tl) {
+                        const int tap = tc * TPC + tl;
                         const int ty = tap / KT, tx = tap % KT;
-                        const int kk = ((ty * S + py) * KS + (tx * S + px)) * CIN + ci;          // first of 8 contiguous weight rows
-                        bulk_g2s(dst + tap * Cfg::PIECE_STRIDE, th + (int64_t)kk * COUT - a_t, Cfg::PIECE_STRIDE, &raw_full[st]);
-                        bulk_g2s(dst + (NTAP + tap) * Cfg::PIECE_STRIDE, nz + (int64_t)kk * COUT - a_n, Cfg::PIECE_STRIDE, &raw_full[st]);
+                        const int kk = ((ty * S + py) * KS + (tx * S + px)) * CIN + ci;          // first of 16 contiguous weight rows
+                        bulk_g2s(dst + tl * Cfg::PIECE_STRIDE, th + (int64_t)kk * COUT - a_t, Cfg::PIECE_STRIDE, &raw_full[st]);
+                        bulk_g2s(dst + (TPC + tl) * Cfg::PIECE_STRIDE, nz + (int64_t)kk * COUT - a_n, Cfg::PIECE_STRIDE, &raw_full[st]);
                     }
-                    S2D_TR(cb < 2 * NG, S2D_EV(cb / NG, g, 1));
+                    S2D_TR(cb < 2 * NCH && c < 16, S2D_EV(cb / NCH, c, 1));
                 }
             }
         }
@@ -292,65 +313,69 @@ conv_s2d_kernel(SlotArgs sa, int64_t off_w, LayerEpi epi, const void* __restrict
             const int a_t = (int)(((uintptr_t)th >> 2) & 3), a_n = (int)(((uintptr_t)nz >> 2) & 3);
             const float s = sa.scale[slot];
             if (IN_U8) mbar_wait(&frame_full[it & 1], (it >> 1) & 1);
-            for (int g = grp; g < NG; g += NGRP) {
-                const uint32_t cb = it * NG + g, st = cb % NSTB;
+            for (int c = grp; c < NCH; c += NGRP) {
+                const int g = c / NCPG;
+                const uint32_t cb = it * NCH + c, st = cb % NSTB;
                 if (IN_U8) {
-                    // ---- the uint8 frame, channel-octet group g = (py, px in {2h, 2h+1}): one pixel pair per unit ----
+                    // ---- the uint8 frame, channel group g = py (all four px phases): plane h holds the pixel pair
+                    // px in {2h, 2h+1}: 8 bytes -> 8 fp16 channels = one 16-byte row ----
                     static_assert(!IN_U8 || (CIN == 4 && S == 4 && HIN == 84), "uint8 staging is written for the 84x84x4 frame stack, stride 4");
                     const uint32_t frame = smem_u32(gFrame + (it & 1) * S2D_FRAME_STRIDE);
-                    const int py = g >> 1, h = g & 1;
+                    const int py = g;
                     mbar_wait(&a_empty[g], (it & 1) ^ 1);
-                    for (int u = tg; u < W * W; u += TG) {
-                        const int yq = u / W, xq = u - yq * W;
+                    for (int u = tg; u < 2 * W * W; u += TG) {
+                        const int h = u / (W * W), pix = u - h * (W * W);
+                        const int yq = pix / W, xq = pix - yq * W;
                         const int y = 4 * yq + py - PAD, x0 = 4 * xq + 2 * h - PAD;
                         if (y >= 0 && y < HIN && x0 >= 0 && x0 < HIN) {
                             uint32_t p0, p1;
                             asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(p0), "=r"(p1) : "r"(frame + (y * HIN + x0) * 4));
-                            const uint32_t dst = sA + g * Cfg::GROUP_BYTES + u * 16;
-                            sts128(dst, make_float4((float)(p0 & 255u), (float)((p0 >> 8) & 255u), (float)((p0 >> 16) & 255u), (float)(p0 >> 24)));
-                            sts128(dst + Cfg::LBO_A, make_float4((float)(p1 & 255u), (float)((p1 >> 8) & 255u), (float)((p1 >> 16) & 255u), (float)(p1 >> 24)));
+                            auto h2 = [](uint32_t lo8, uint32_t hi8) {        // two bytes -> two fp16 (exact)
+                                return (uint32_t)__half_as_ushort(__ushort2half_rn((unsigned short)lo8)) |
+                                       ((uint32_t)__half_as_ushort(__ushort2half_rn((unsigned short)hi8)) << 16);
+                            };
+                            const uint4 row = make_uint4(h2(p0 & 255u, (p0 >> 8) & 255u), h2((p0 >> 16) & 255u, p0 >> 24),
+                                                         h2(p1 & 255u, (p1 >> 8) & 255u), h2((p1 >> 16) & 255u, p1 >> 24));
+                            sts128u(sA + g * Cfg::GROUP_BYTES + h * Cfg::LBO_A + pix * 16, row);
                         }
                     }
                     fence_proxy_async_smem();
                     __syncwarp();
                     if (lane == 0) {
                         mbar_arrive(&a_full[g]);
-                        if (g + NGRP >= NG) mbar_arrive(&frame_empty[it & 1]);     // this warp's last read of the raw frame
+                        if (c + NGRP >= NCH) mbar_arrive(&frame_empty[it & 1]);    // this warp's last read of the raw frame
                     }
                 }
-                S2D_TR(tg == 0 && it < 2, S2D_EV(it, g, 7));
+                S2D_TR(tg == 0 && it < 2 && c < 16, S2D_EV(it, c, 7));
                 mbar_wait(&raw_full[st], (cb / NSTB) & 1);
-                S2D_TR(tg == 0 && it < 2, S2D_EV(it, g, 2));
+                S2D_TR(tg == 0 && it < 2 && c < 16, S2D_EV(it, c, 2));
                 const uint32_t sBs = sB + st * Cfg::BST_BYTES;
-                float w[Cfg::B_UPT][4];
+                float w[Cfg::B_UPT][8];
 #pragma unroll
                 for (int i = 0; i < Cfg::B_UPT; ++i) {
-                    const int kq = kq0 + i * KQ_STEP;            // local k quad: tap = kq >> 1, rows 4*(kq & 1) .. +3 of the tap's piece
-                    if (kq < NTAP * 2) {
-                        const uint32_t pt = sBs + (kq >> 1) * Cfg::PIECE_STRIDE + (uint32_t)((a_t + (4 * (kq & 1)) * COUT + n) * 4);
-                        const uint32_t pn = sBs + (NTAP + (kq >> 1)) * Cfg::PIECE_STRIDE + (uint32_t)((a_n + (4 * (kq & 1)) * COUT + n) * 4);
+                    const int kp = kq0 + i * KQ_STEP;            // local k octet: tap kp >> 1 of the chunk, rows 8*(kp & 1) .. +7 of its piece
+                    if (kp < TPC * 2) {
+                        const uint32_t pt = sBs + (kp >> 1) * Cfg::PIECE_STRIDE + (uint32_t)((a_t + (8 * (kp & 1)) * COUT + n) * 4);
+                        const uint32_t pn = sBs + (TPC + (kp >> 1)) * Cfg::PIECE_STRIDE + (uint32_t)((a_n + (8 * (kp & 1)) * COUT + n) * 4);
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) w[i][j] = perturbed(lds32(pt + j * COUT * 4), s, lds32(pn + j * COUT * 4));
+                        for (int j = 0; j < 8; ++j) w[i][j] = perturbed(lds32(pt + j * COUT * 4), s, lds32(pn + j * COUT * 4));
                     }
                 }
                 named_bar_sync(3 + grp, TG);                     // every raw value of the stage is in registers: overwrite it
 #pragma unroll
                 for (int i = 0; i < Cfg::B_UPT; ++i) {
-                    const int kq = kq0 + i * KQ_STEP;
-                    if (kq < NTAP * 2) {
-                        float4 hi, lo;
-                        split_tf32_fast(w[i][0], hi.x, lo.x);
-                        split_tf32_fast(w[i][1], hi.y, lo.y);
-                        split_tf32_fast(w[i][2], hi.z, lo.z);
-                        split_tf32_fast(w[i][3], hi.w, lo.w);
-                        sts128(sBs + kq * Cfg::LBO_B + n * 16, hi);
-                        sts128(sBs + kq * Cfg::LBO_B + (COUT + n) * 16, lo);
+                    const int kp = kq0 + i * KQ_STEP;
+                    if (kp < TPC * 2) {
+                        uint4 hi, lo;
+                        split_f16x8(w[i], hi, lo);
+                        sts128u(sBs + kp * Cfg::LBO_B + n * 16, hi);
+                        sts128u(sBs + kp * Cfg::LBO_B + (COUT + n) * 16, lo);
                     }
                 }
                 fence_proxy_async_smem();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&b_full[st]);
-                S2D_TR(tg == 0 && it < 2, S2D_EV(it, g, 3));
+                S2D_TR(tg == 0 && it < 2 && c < 16, S2D_EV(it, c, 3));
             }
             ++it;
         }
@@ -376,16 +401,16 @@ conv_s2d_kernel(SlotArgs sa, int64_t off_w, LayerEpi epi, const void* __restrict
             float* outp = so.base + slot * so.slot_stride;
             if (so.next_img) {
                 // zero padding of the next layer's image: pixels (Y, X) of its padded grid that no output maps to
-                const int nHP = so.nHP, nq = COUT / 4;
+                const int nHP = so.nHP, no = COUT / 8;
                 for (int b = et; b < nHP * nHP; b += S2D_EPI_THREADS) {
                     const int Y = b / nHP, X = b - Y * nHP;
                     if (Y >= so.nPADB && Y < so.nPADB + HOUT && X >= so.nPADB && X < so.nPADB + HOUT) continue;
                     const int pix = (Y / so.nS) * so.nW + (X / so.nS), pp = (Y % so.nS) * so.nS + (X % so.nS);
-                    for (int q = 0; q < nq; ++q) {
-                        const int cq = pp * nq + q;                                   // channel quad of the next image
-                        float4* p = reinterpret_cast<float4*>(outp) + (size_t)((cq >> 1) * 4 + (cq & 1)) * so.nPIXP + pix;
-                        p[0] = make_float4(0.f, 0.f, 0.f, 0.f);
-                        p[(size_t)2 * so.nPIXP] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    for (int q = 0; q < no; ++q) {
+                        const int co = pp * no + q;                                   // channel octet of the next image
+                        uint4* p = reinterpret_cast<uint4*>(outp) + (size_t)((co >> 1) * 4 + (co & 1)) * so.nPIXP + pix;
+                        p[0] = make_uint4(0u, 0u, 0u, 0u);
+                        p[(size_t)2 * so.nPIXP] = make_uint4(0u, 0u, 0u, 0u);
                     }
                 }
             }
@@ -413,7 +438,7 @@ conv_s2d_kernel(SlotArgs sa, int64_t off_w, LayerEpi epi, const void* __restrict
                         const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
                         for (int y = 0; y < 4; ++y) {
-                            float r = __uint_as_float(__float_as_uint(v[x + y])) + v2[x + y];
+                            float r = fmaf(v2[x + y], F16_LO_INV, v[x + y]);        // main + 2^-11 * correction accumulator
                             if (IN_U8) r *= IN_SCALE;
                             r += bb[y];
                             if (bn) r = (r - s_mean[n0 + x + y]) * s_inv[n0 + x + y] * s_gamma[n0 + x + y] + s_beta[n0 + x + y];   // policies.py:322
@@ -425,17 +450,15 @@ conv_s2d_kernel(SlotArgs sa, int64_t off_w, LayerEpi epi, const void* __restrict
 #pragma unroll
                         for (int x = 0; x < 16; x += 4) dst[x / 4] = make_float4(v[x], v[x + 1], v[x + 2], v[x + 3]);
                         if (so.xc) {
-                            const int kq0 = ((oy * HOUT + ox) * COUT + n0) >> 2;
-                            float4* xp = reinterpret_cast<float4*>(so.xc) + ((int64_t)(slot >> 7) * so.xc_kq + kq0) * 256 + (slot & 127);
+                            const int ko0 = ((oy * HOUT + ox) * COUT + n0) >> 3;
+                            uint4* xp = reinterpret_cast<uint4*>(so.xc) + ((int64_t)(slot >> 7) * so.xc_ko + ko0) * 256 + (slot & 127);
 #pragma unroll
-                            for (int x = 0; x < 16; x += 4) {
-                                float4 hi, lo;
-                                split_tf32_fast(v[x], hi.x, lo.x);
-                                split_tf32_fast(v[x + 1], hi.y, lo.y);
-                                split_tf32_fast(v[x + 2], hi.z, lo.z);
-                                split_tf32_fast(v[x + 3], hi.w, lo.w);
-                                xp[(x / 4) * 256] = hi;
-                                xp[(x / 4) * 256 + 128] = lo;
+                            for (int x = 0; x < 16; x += 8) {
+                                const float e[8] = {v[x], v[x + 1], v[x + 2], v[x + 3], v[x + 4], v[x + 5], v[x + 6], v[x + 7]};
+                                uint4 hi, lo;
+                                split_f16x8(e, hi, lo);
+                                xp[(x / 8) * 256] = hi;
+                                xp[(x / 8) * 256 + 128] = lo;
                             }
                         }
                     } else {
@@ -443,14 +466,12 @@ conv_s2d_kernel(SlotArgs sa, int64_t off_w, LayerEpi epi, const void* __restrict
                         const int pix = (Y / so.nS) * so.nW + (X / so.nS);
                         const int pp = (Y % so.nS) * so.nS + (X % so.nS);
 #pragma unroll
-                        for (int x = 0; x < 16; x += 4) {
-                            const int cq = pp * (COUT / 4) + (n0 + x) / 4;
-                            float4 hi, lo;
-                            split_tf32_fast(v[x], hi.x, lo.x);
-                            split_tf32_fast(v[x + 1], hi.y, lo.y);
-                            split_tf32_fast(v[x + 2], hi.z, lo.z);
-                            split_tf32_fast(v[x + 3], hi.w, lo.w);
-                            float4* p = reinterpret_cast<float4*>(outp) + (size_t)((cq >> 1) * 4 + (cq & 1)) * so.nPIXP + pix;
+                        for (int x = 0; x < 16; x += 8) {
+                            const int co = pp * (COUT / 8) + (n0 + x) / 8;            // channel octet of the next image
+                            const float e[8] = {v[x], v[x + 1], v[x + 2], v[x + 3], v[x + 4], v[x + 5], v[x + 6], v[x + 7]};
+                            uint4 hi, lo;
+                            split_f16x8(e, hi, lo);
+                            uint4* p = reinterpret_cast<uint4*>(outp) + (size_t)((co >> 1) * 4 + (co & 1)) * so.nPIXP + pix;
                             p[0] = hi;
                             p[(size_t)2 * so.nPIXP] = lo;
                         }
@@ -517,7 +538,7 @@ int dne_launch_conv_layer_s2d(const SlotArgs& sa, const dne_layer_desc& L, const
                               int n_slots, int sm_count, cudaStream_t st, float* xc) {
     S2dOut so;
     so.xc = next ? nullptr : xc;
-    so.xc_kq = (L.hout * L.hout * L.cout) / 4;
+    so.xc_ko = (L.hout * L.hout * L.cout) / 8;
     so.base = out;
     so.slot_stride = out_slot_stride;
     so.next_img = next ? 1 : 0;

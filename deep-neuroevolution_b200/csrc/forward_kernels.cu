@@ -666,6 +666,7 @@ DensePlan dne_plan_dense(const dne_layer_desc& L, int n_slots, int paired, bool 
     if (split > k_tiles) split = k_tiles;
     if (split < 1) split = 1;
     int kt_per = (k_tiles + split - 1) / split;
+    kt_per += kt_per & 1;                                // k_per_split % 32 == 0: the TMA-fed fp16 GEMM moves K chunks of 32
     p.k_per_split = kt_per * DG_BK;
     p.n_split = (K + p.k_per_split - 1) / p.k_per_split;
     p.rows_per_chunk = pick_rows_per_chunk(K, N);

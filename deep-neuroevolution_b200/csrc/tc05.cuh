@@ -8,6 +8,7 @@
 // Consecutive rows are consecutive 16-byte chunks, so staging threads that own consecutive rows write conflict-free.
 #pragma once
 #include <cuda_runtime.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 
 namespace tc05 {
@@ -67,6 +68,14 @@ __host__ __device__ constexpr uint32_t idesc_tf32(int M, int N) {
            | ((uint32_t)(M >> 4) << 24);  // m_dim
 }
 
+// instruction descriptor: kind::f16 with fp16 operands, fp32 accumulate, A and B K-major, dense (K = 16 per instruction)
+__host__ __device__ constexpr uint32_t idesc_f16(int M, int N) {
+    return (1u << 4)                      // c_format = F32
+                                          // a_format = b_format = F16 (0)
+           | ((uint32_t)(N >> 3) << 17)   // n_dim
+           | ((uint32_t)(M >> 4) << 24);  // m_dim
+}
+
 // Explicit shared-window accesses with 32-bit addresses.  Stores through a C++ pointer derived from the (re-aligned)
 // dynamic shared-memory base compile to GENERIC ST.E / LD.E (the cast hides the address space from ptxas).
 __device__ __forceinline__ void sts128(uint32_t saddr, const float4& v) {
@@ -100,6 +109,15 @@ __device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t adesc, uint64
         ".reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void mma_f16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
         "}\n" ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
@@ -152,6 +170,30 @@ __device__ __forceinline__ void split_tf32_fast(float x, float& hi, float& lo) {
     const uint32_t hb = (__float_as_uint(x) + 0x1000u) & 0xFFFFE000u;
     hi = __uint_as_float(hb);
     lo = __uint_as_float(__float_as_uint(x - hi) & 0xFFFFE000u);
+}
+
+// ---- 2 x fp16 operand split (kind::f16 runs at twice the MAC rate of kind::tf32) ----------------------------------------
+// x = h0 + h1 * 2^-11 with h0 = rn_fp16(x), h1 = rn_fp16((x - h0) * 2^11): 22 significand bits, |error| <= 2^-24 |x| (fp16
+// subnormals are exact to 2^-25 absolute and h1 picks up the rest).  The lo part is carried SCALED by 2^11 so that it never
+// falls into fp16's subnormal range before x itself does; products with it go to a separate accumulator that the epilogue
+// folds back with 2^-11:  a*b ~= h0a*h0b + 2^-11 * (h0a*h1b + h1a*h0b)   (dropped h1a*h1b term: 2^-24 relative).
+// fp16 products are exact in the fp32 accumulator.  Range: |x| <= 65504 (fp16 max); larger magnitudes saturate.
+constexpr float F16_LO_SCALE = 2048.0f, F16_LO_INV = 1.0f / 2048.0f;
+__device__ __forceinline__ void split_f16(float x, __half& h0, __half& h1) {
+    h0 = __float2half_rn(fminf(fmaxf(x, -65504.0f), 65504.0f));
+    h1 = __float2half_rn((x - __half2float(h0)) * F16_LO_SCALE);
+}
+// eight values -> one 16-byte row of the hi plane and one of the (scaled) lo plane
+__device__ __forceinline__ void split_f16x8(const float (&x)[8], uint4& hi, uint4& lo) {
+    __half h[8], l[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) split_f16(x[i], h[i], l[i]);
+    auto pk = [](__half a, __half b) { return (uint32_t)__half_as_ushort(a) | ((uint32_t)__half_as_ushort(b) << 16); };
+    hi = make_uint4(pk(h[0], h[1]), pk(h[2], h[3]), pk(h[4], h[5]), pk(h[6], h[7]));
+    lo = make_uint4(pk(l[0], l[1]), pk(l[2], l[3]), pk(l[4], l[5]), pk(l[6], l[7]));
+}
+__device__ __forceinline__ void sts128u(uint32_t saddr, const uint4& v) {
+    asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
 }  // namespace tc05

@@ -4,15 +4,17 @@
 //
 // The r01 kernel (tc_conv.cu: theta_gemm_tc_kernel, 31 us per 256-slot LargeModel tick) staged both operands through the
 // threads (global -> registers -> TF32 split -> st.shared) with two stages and a block barrier per 16-wide chunk.  Here
-// both operands already exist in global memory in the UMMA K-major canonical layout, split into TF32 hi / lo parts:
+// both operands already exist in global memory in the UMMA K-major canonical layout, as 2 x fp16 splits (tc05.cuh:
+// x = h0 + h1*2^-11; kind::f16 runs at twice the MAC rate of kind::tf32 and the operands are half the bytes):
 //   * W changes once per generation: dne_theta_prepare() relays it out (theta_prep_kernel) into
-//       Wc[n tile of 128][k quad][hi | lo][128 n][4 k]      one k-quad plane = [B_hi ; B_lo] stacked along N = 4 KB
+//       Wc[n tile of 128][k octet][h0 | h1][128 n][8 k]     one k-octet plane = [B_h0 ; B_h1] stacked along N = 4 KB
 //   * X is the output of the last convolution: its epilogue (conv_s2d.cu) writes, besides the NHWC vector the noise GEMV
 //     streams, the same values as
-//       Xc[m tile of 128][k quad][hi | lo][128 slots][4 k]  one k-quad plane = [A_hi ; A_lo] = 4 KB
-// so a K chunk of 16 of either operand is one contiguous 16 KB run and the whole main loop is: one producer thread issuing
-// cp.async.bulk into a 4-stage ring, one MMA thread issuing tcgen05.mma (3xTF32: A_hi*[B_hi;B_lo] as one N = 256 MMA plus
-// A_lo*B_hi), no staging threads at all.  A CTA owns BOTH 128-row M tiles of a 128-column N tile (the B chunk is read
+//       Xc[m tile of 128][k octet][h0 | h1][128 slots][8 k] one k-octet plane = [A_h0 ; A_h1] = 4 KB
+// so a K chunk of 32 of either operand is one contiguous 16 KB run and the whole main loop is: one producer thread issuing
+// cp.async.bulk into a 4-stage ring, one MMA thread issuing tcgen05.mma (A_h0*[B_h0;B_h1] as one N = 256 MMA into
+// [main | correction] accumulator columns plus A_h1*B_h0 into the correction columns; result = main + 2^-11 * correction),
+// no staging threads at all.  A CTA owns BOTH 128-row M tiles of a 128-column N tile (the B chunk is read
 // once for 256 slots; 2 x 256 accumulator columns = the whole TMEM) and one K split; partials are deterministic.
 // The N tiles of one K split form a thread-block cluster: every CTA fetches 1/CL of the shared A chunk and MULTICASTS it
 // into all CL CTAs' stages (cp.async.bulk ... .multicast::cluster), so X crosses the L2 -> SM fabric once per split instead
@@ -26,9 +28,9 @@ using namespace tc05;
 
 int g_dne_theta_mc = 0;
 namespace {
-constexpr int TGM_KC = 16, TGM_STAGES = 4;
+constexpr int TGM_KC = 32, TGM_STAGES = 4;                 // 32 k = four k-octet planes per chunk
 constexpr int TGM_PLANE = 256 * 16;                         // bytes of one k-quad plane: 128 hi rows + 128 lo rows
-constexpr int TGM_CHUNK = (TGM_KC / 4) * TGM_PLANE;         // 16 KB per operand tile and chunk
+constexpr int TGM_CHUNK = (TGM_KC / 8) * TGM_PLANE;         // 16 KB per operand tile and chunk
 constexpr int TGM_EPI_WARPS = 8;
 constexpr int TGM_THREADS = 32 * (2 + TGM_EPI_WARPS);
 
@@ -109,7 +111,7 @@ theta_gemm_tma_kernel(const float* __restrict__ Xc, const float* __restrict__ Wc
         }
     } else if (warp == 1) {
         // ===== MMA issuer (converged warp, one elected lane) =====
-        constexpr uint32_t IDESC2 = idesc_tf32(128, 256), IDESC1 = idesc_tf32(128, 128);
+        constexpr uint32_t IDESC2 = idesc_f16(128, 256), IDESC1 = idesc_f16(128, 128);
         const uint64_t d0 = smem_desc(smem_u32(smem), TGM_PLANE, 128);
         for (int i = 0; i < nc; ++i) {
             const int st = i % TGM_STAGES;
@@ -118,14 +120,14 @@ theta_gemm_tma_kernel(const float* __restrict__ Xc, const float* __restrict__ Wc
             if (elect_one()) {
                 const uint64_t ds = d0 + (uint64_t)((st * STAGE) >> 4);
 #pragma unroll
-                for (int k8 = 0; k8 < TGM_KC / 8; ++k8) {
-                    const uint64_t dB = ds + (uint64_t)((MT * TGM_CHUNK + 2 * k8 * TGM_PLANE) >> 4);
+                for (int k16 = 0; k16 < TGM_KC / 16; ++k16) {
+                    const uint64_t dB = ds + (uint64_t)((MT * TGM_CHUNK + 2 * k16 * TGM_PLANE) >> 4);
 #pragma unroll
                     for (int mt = 0; mt < MT; ++mt) {
-                        const uint64_t dAh = ds + (uint64_t)((mt * TGM_CHUNK + 2 * k8 * TGM_PLANE) >> 4);
+                        const uint64_t dAh = ds + (uint64_t)((mt * TGM_CHUNK + 2 * k16 * TGM_PLANE) >> 4);
                         const uint32_t d = tmem_base + mt * 256;
-                        mma_tf32(d, dAh, dB, IDESC2, (i | k8) != 0);                    // A_hi * [B_hi ; B_lo]
-                        mma_tf32(d, dAh + (uint64_t)(2048 >> 4), dB, IDESC1, 1);         // A_lo * B_hi
+                        mma_f16(d, dAh, dB, IDESC2, (i | k16) != 0);                    // A_h0 * [B_h0 ; B_h1] -> [main | correction]
+                        mma_f16(d + 128, dAh + (uint64_t)(2048 >> 4), dB, IDESC1, 1);    // A_h1 * B_h0 -> correction
                     }
                 }
                 if (CL == 1) mma_commit(&empty_bar[st]);
@@ -135,7 +137,7 @@ theta_gemm_tma_kernel(const float* __restrict__ Xc, const float* __restrict__ Wc
             __syncwarp();
         }
     } else {
-        // ===== epilogue: part[split][m][n] = D[:, n] + D[:, 128 + n] =====
+        // ===== epilogue: part[split][m][n] = D[:, n] + 2^-11 * D[:, 128 + n] =====
         const int ew = warp - 2, lq = warp & 3, half = ew >> 2;       // TMEM lane quarter = warp % 4 (hardware rule)
         if (nc > 0) {
             mbar_wait(&done_bar, 0);
@@ -163,10 +165,11 @@ theta_gemm_tma_kernel(const float* __restrict__ Xc, const float* __restrict__ Wc
                 for (int x = 0; x < 16; x += 4) {
                     if (n + x + 3 < N)
                         *reinterpret_cast<float4*>(P + (int64_t)m * N + n + x) =
-                            make_float4(v[x] + v2[x], v[x + 1] + v2[x + 1], v[x + 2] + v2[x + 2], v[x + 3] + v2[x + 3]);
+                            make_float4(fmaf(v2[x], F16_LO_INV, v[x]), fmaf(v2[x + 1], F16_LO_INV, v[x + 1]),
+                                        fmaf(v2[x + 2], F16_LO_INV, v[x + 2]), fmaf(v2[x + 3], F16_LO_INV, v[x + 3]));
                     else
                         for (int y = 0; y < 4; ++y)
-                            if (n + x + y < N) P[(int64_t)m * N + n + x + y] = v[x + y] + v2[x + y];
+                            if (n + x + y < N) P[(int64_t)m * N + n + x + y] = fmaf(v2[x + y], F16_LO_INV, v[x + y]);
                 }
             }
         }
@@ -177,37 +180,34 @@ theta_gemm_tma_kernel(const float* __restrict__ Xc, const float* __restrict__ Wc
     if (warp == 0) tmem_dealloc(tmem_base, TCOLS);
 }
 
-// W[K][N] (row-major, arbitrary element alignment) -> Wc[n tile][k quad][hi | lo][128][4]; columns >= N are zero
-__global__ void theta_prep_kernel(const float* __restrict__ W, int K, int N, int KQ, float* __restrict__ Wc) {
-    const int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;      // (ntile, kq, n)
+// W[K][N] (row-major, arbitrary element alignment) -> Wc[n tile][k octet][h0 | h1][128][8 x fp16]; columns >= N are zero
+__global__ void theta_prep_kernel(const float* __restrict__ W, int K, int N, int KO, float* __restrict__ Wc) {
+    const int64_t u = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;      // (ntile, ko, n)
     const int n_tiles = (N + 127) / 128;
-    if (u >= (int64_t)n_tiles * KQ * 128) return;
+    if (u >= (int64_t)n_tiles * KO * 128) return;
     const int nl = (int)(u % 128);
-    const int kq = (int)((u / 128) % KQ), nt = (int)(u / ((int64_t)128 * KQ));
+    const int ko = (int)((u / 128) % KO), nt = (int)(u / ((int64_t)128 * KO));
     const int n = nt * 128 + nl;
-    float w[4];
+    float w[8];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) w[j] = (n < N && 4 * kq + j < K) ? W[(int64_t)(4 * kq + j) * N + n] : 0.0f;
-    float4 hi, lo;
-    split_tf32_fast(w[0], hi.x, lo.x);
-    split_tf32_fast(w[1], hi.y, lo.y);
-    split_tf32_fast(w[2], hi.z, lo.z);
-    split_tf32_fast(w[3], hi.w, lo.w);
-    float4* dst = reinterpret_cast<float4*>(Wc) + ((int64_t)nt * KQ + kq) * 256 + nl;
+    for (int j = 0; j < 8; ++j) w[j] = (n < N && 8 * ko + j < K) ? W[(int64_t)(8 * ko + j) * N + n] : 0.0f;
+    uint4 hi, lo;
+    split_f16x8(w, hi, lo);
+    uint4* dst = reinterpret_cast<uint4*>(Wc) + ((int64_t)nt * KO + ko) * 256 + nl;
     dst[0] = hi;
     dst[128] = lo;
 }
 }  // namespace
 
 // ---- host interface (forward.cuh) ---------------------------------------------------------------------------------
-size_t dne_tgm_xc_bytes(int n_slots, int K) { return (size_t)((n_slots + 127) / 128) * (K / 4) * TGM_PLANE; }
-size_t dne_tgm_wc_bytes(int K, int N) { return (size_t)((N + 127) / 128) * (K / 4) * TGM_PLANE; }
+size_t dne_tgm_xc_bytes(int n_slots, int K) { return (size_t)((n_slots + 127) / 128) * (K / 8) * TGM_PLANE; }
+size_t dne_tgm_wc_bytes(int K, int N) { return (size_t)((N + 127) / 128) * (K / 8) * TGM_PLANE; }
 bool dne_tgm_supported(int K, int N, int k_per_split) { return K % TGM_KC == 0 && N % 4 == 0 && k_per_split % TGM_KC == 0; }
 
 int dne_launch_theta_prep(const float* W, int K, int N, float* Wc, cudaStream_t st) {
-    const int KQ = K / 4;
-    const int64_t units = (int64_t)((N + 127) / 128) * KQ * 128;
-    theta_prep_kernel<<<(unsigned)((units + 255) / 256), 256, 0, st>>>(W, K, N, KQ, Wc);
+    const int KO = K / 8;
+    const int64_t units = (int64_t)((N + 127) / 128) * KO * 128;
+    theta_prep_kernel<<<(unsigned)((units + 255) / 256), 256, 0, st>>>(W, K, N, KO, Wc);
     DNE_LAUNCHED(1);
     return 0;
 }
@@ -244,7 +244,7 @@ static int launch_tgm(const float* Xc, const float* Wc, int M, int N, int KQ, in
 int dne_launch_theta_gemm_tma(const float* Xc, const float* Wc, int M, int K, int N, int k_per_split, int n_split, float* part,
                               cudaStream_t st) {
     if (!dne_tgm_supported(K, N, k_per_split)) return DNE_ERR_UNSUP;
-    const int KQ = K / 4, n_chunks = K / TGM_KC, cps = k_per_split / TGM_KC;
+    const int KQ = K / 8, n_chunks = K / TGM_KC, cps = k_per_split / TGM_KC;      // KQ: k-octet planes
     const int m_tiles = (M + 127) / 128, n_tiles = (N + 127) / 128;
     if (m_tiles > 1 && (m_tiles & 1)) return DNE_ERR_UNSUP;          // M tiles come in pairs (one CTA owns two) or alone
 #define TGM_ARGS Xc, Wc, M, N, KQ, cps, n_chunks, n_split, (m_tiles >= 2 ? m_tiles / 2 : 1), n_tiles, part, st

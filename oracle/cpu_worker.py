@@ -81,6 +81,12 @@ def _worker(args):
     import torch
     torch.set_num_threads(1)                                    # es.py:91 / scripts/launch.py:117
     wid, pair_idx, T, sigma, seed = args
+    cores = _G.get("cores")
+    if cores:                                                   # one worker per core: no migration, and the member weights the
+        try:                                                    # worker allocates below are first-touched on its own NUMA node
+            os.sched_setaffinity(0, {cores[wid % len(cores)]})
+        except (AttributeError, OSError):
+            pass
     net, noise, theta = _G["net"], _G["noise"], _G["theta"]
     rs = np.random.RandomState(seed + wid)
     obs_pool = rs.randint(0, 256, size=(16, 1, 84, 84, 4)).astype(np.uint8)
@@ -121,7 +127,11 @@ def measure_workers(net_name: str, noise: np.ndarray, theta: np.ndarray, idx: Li
     import torch                      # import in the parent so the forked workers do not each pay the cold import
     torch.set_num_threads(1)
     net = O.make_net(net_name)
-    _G.update(net=net, noise=noise, theta=theta)
+    try:
+        cores = sorted(os.sched_getaffinity(0))
+    except AttributeError:
+        cores = None
+    _G.update(net=net, noise=noise, theta=theta, cores=cores)
     if use_ref_batch:
         _G["ref_batch"] = np.random.RandomState(seed).randint(0, 256, size=(128, 84, 84, 4)).astype(np.uint8)
     else:

@@ -91,21 +91,22 @@ def test_conv_tc_vs_simt_vs_oracle(ctx, host_noise, name):
 
 
 def _s2d_geom(l):
-    """Image geometry of a conv layer's INPUT on the shifted-window path (csrc/conv_s2d.cu: s2d_geom)."""
+    """Image geometry of a conv layer's INPUT on the shifted-window path (csrc/conv_s2d.cu: s2d_geom): planes of 8 fp16
+    channels per pixel, groups of 16 channels = [h0 plane 0, h0 plane 1, h1 plane 0, h1 plane 1]."""
     hp = (l.hout - 1) * l.stride + l.ksize
     W = hp // l.stride
     cp = l.stride * l.stride * l.cin
     pixp = (W * W + 7) // 8 * 8
-    return dict(S=l.stride, pad=l.pad, W=W, NG=cp // 8, PIXP=pixp, floats=(cp // 8) * 4 * pixp * 4)
+    return dict(S=l.stride, pad=l.pad, W=W, NG=cp // 16, PIXP=pixp, floats=(cp // 16) * 4 * pixp * 4)
 
 
 def _decode_image(buf, l):
-    """[NG][hi/lo][2 channel quads][PIXP][4] floats -> the NHWC activation [hin, hin, cin] it encodes (hi + lo), and
-    the zero padding it must carry."""
+    """[NG][h0 / h1][2 channel octets][PIXP][8 x fp16] -> the NHWC activation [hin, hin, cin] it encodes
+    (h0 + h1 * 2^-11), and the largest magnitude in the zero padding it must carry."""
     g = _s2d_geom(l)
-    img = buf[:g["floats"]].reshape(g["NG"], 2, 2, g["PIXP"], 4).astype(np.float64)
-    full = img[:, 0] + img[:, 1]                                     # [NG][2][PIXP][4]
-    chans = full.transpose(2, 0, 1, 3).reshape(g["PIXP"], g["NG"] * 8)[:g["W"] * g["W"]]      # [pixel][s2d channel]
+    raw = buf[:g["floats"]].view(np.float16).reshape(g["NG"], 2, 2, g["PIXP"], 8).astype(np.float64)
+    full = raw[:, 0] + raw[:, 1] / 2048.0                            # [NG][2][PIXP][8]
+    chans = full.transpose(2, 0, 1, 3).reshape(g["PIXP"], g["NG"] * 16)[:g["W"] * g["W"]]     # [pixel][s2d channel]
     S, W = g["S"], g["W"]
     grid = chans.reshape(W, W, S, S, l.cin).transpose(0, 2, 1, 3, 4).reshape(W * S, W * S, l.cin)   # padded NHWC
     inner = grid[g["pad"]:g["pad"] + l.hin, g["pad"]:g["pad"] + l.hin]
@@ -117,7 +118,7 @@ def _decode_image(buf, l):
 @pytest.mark.parametrize("conv_tc", [2, 1])
 def test_conv_tc_intermediate_activations(ctx, host_noise, conv_tc):
     """Layer-by-layer check of the tensor-core convolutions (conv3 output = the 7744-vector fed to the fc layer).
-    conv_tc = 2: shifted-window kernels -- conv1 / conv2 write the NEXT layer's space-to-depth image (TF32 hi/lo planes,
+    conv_tc = 2: shifted-window kernels -- conv1 / conv2 write the NEXT layer's space-to-depth image (fp16 h0/h1 planes,
     zero padded), decoded here; conv_tc = 1: NHWC activations of the im2col-staged kernels."""
     net, net_o = N.make_net("LargeModel"), O.make_net("LargeModel")
     P = net.num_params

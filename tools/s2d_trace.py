@@ -26,7 +26,7 @@ L.dne_debug_s2d_trace.argtypes = [C.c_void_p]
 buf = (C.c_longlong * (3 * 512))()
 assert L.dne_debug_s2d_trace(buf) == 0
 tr = np.array(buf, dtype=np.int64).reshape(3, 512)
-NG = [8, 16, 8]
+NG = [4, 16, 12]   # chunks per member (conv1, conv2, conv3)
 names = ["wprod:slot free", "wprod:issued", "conv:raw landed", "conv:tile ready", "mma:A ready", "mma:B ready", "mma:issued", "conv:A staged/begin"]
 for l in range(3):
     t = tr[l]; t0 = t[0]
