@@ -44,7 +44,10 @@ def parse():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference", "cpu-sample"])
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference", "cpu-sample", "gpu-ref-proxy"])
+    ap.add_argument("--workload", default="es", choices=["es", "mlp", "ga", "nsr"],
+                    help="es = BASELINE.json configs[1] (the contract's default line); mlp / ga / nsr = configs[4] / [2] / [3] "
+                         "(bench_workloads.py), same JSON contract")
     ap.add_argument("--episode-len", type=int, default=int(os.environ.get("DNE_BENCH_T", 1000)))
     ap.add_argument("--pop", type=int, default=POP)
     ap.add_argument("--slots", type=int, default=SLOTS)
@@ -181,7 +184,7 @@ def run_b200(args):
     ev_ptr = [C.c_void_p(e.cuda_event) for e in phase_ev]
 
     KERNELS_PER_TICK = 6          # conv1-3, theta GEMM, noise GEMV, combine+head (LargeModel, default options)
-    USE_GRAPH = os.environ.get("DNE_BENCH_GRAPH", "0") == "1"
+    USE_GRAPH = os.environ.get("DNE_BENCH_GRAPH", "1") == "1"       # r02 A/B at T=200: 639K vs 612K env-steps/s
     PROF_EVERY = 16 if USE_GRAPH else 1
     graphs = {}
     prof_state = {"on": False}
@@ -560,5 +563,11 @@ if __name__ == "__main__":
         _emit(cpu_sample(a))
     elif a.impl == "reference":
         run_reference(a)
+    elif a.impl == "gpu-ref-proxy":
+        import bench_workloads
+        bench_workloads.run_gpu_ref_proxy(a, _emit, ClockSampler)
+    elif a.workload != "es":
+        import bench_workloads
+        bench_workloads.run(a, _emit, ClockSampler, load_peaks)
     else:
         run_b200(a)

@@ -273,3 +273,88 @@ def run(args, emit, ClockSampler, load_peaks):
               "roofline": roofline, "cpu_baseline": None})
     if world > 1:
         dist.destroy_process_group()
+
+
+def run_gpu_ref_proxy(args, emit, ClockSampler):
+    """--impl gpu-ref-proxy: a PROXY of the reference's GPU schedule (gpu_implementation/) on this GPU, for the
+    north_star's "vs gpu_implementation" denominator.  TensorFlow, the gym_tensorflow ops and ALE are absent, so this is not
+    the reference itself; it reproduces the schedule's data movement with library kernels (torch -> cuBLAS batched GEMM):
+      * every member's FULL weight vector is materialised in device memory and (re)loaded by a 4*P-byte host->device copy
+        per member and episode (neuroevolution/models/base.py:158-192 `load` -> scatter_update; concurrent_worker.py:72-102),
+      * per tick one batched matmul per layer over all resident members -- the conv layers as extract_image_patches +
+        batched matmul, the dense layers as batched mat-vec (gym_tensorflow/ops/indexedmatmul.cpp:169-202: SgemmBatched over
+        host-built pointer arrays; models/base.py:54-99) -- i.e. every member streams its own 16.2 MB of weights per tick
+        (no antithetic sharing, no split of theta and noise),
+      * argmax on the device, synthetic observations / rewards resident in HBM (as in the b200 arm's `value`).
+    What it leaves out (all in the reference's disfavour): TF op dispatch, the per-call host pointer-array build + H2D,
+    the CPU env thread pool, the master's numpy update.  So it is a LOWER bound on the reference schedule's time here."""
+    import torch
+    import torch.nn.functional as Fn
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(0)
+    T, pop, slots = args.episode_len, args.pop, args.slots
+    shapes = [(8, 4, 32, 4, 2, 2), (4, 32, 64, 2, 1, 2), (3, 64, 64, 1, 1, 1)]       # k, cin, cout, stride, pad_before, pad_after
+    sizes = [8 * 8 * 4 * 32, 32, 4 * 4 * 32 * 64, 64, 3 * 3 * 64 * 64, 64, 7744 * 512, 512, 512 * 18, 18]
+    P = sum(sizes)
+    W = torch.randn(slots, P, device=dev) * 0.05                                     # [members, P]: materialised weights
+    host = [torch.randn(P).pin_memory() for _ in range(8)]                          # rotating pinned sources of the member loads
+    offs = np.cumsum([0] + sizes)
+    pool = torch.randint(0, 256, (4, slots, 84, 84, 4), dtype=torch.uint8, device=dev)
+    rew = (torch.rand(64, slots, device=dev) < 0.05).float() * 10.0
+    ret = torch.zeros(slots, device=dev)
+
+    def view(i, *shape):
+        return W[:, offs[i]:offs[i + 1]].view(slots, *shape)
+
+    def tick(t):
+        x = pool[t & 3].permute(0, 3, 1, 2).float() / 255.0                          # NCHW
+        for li, (k, cin, cout, s, pb, pa) in enumerate(shapes):
+            xp = Fn.pad(x, (pb, pa, pb, pa))
+            patches = Fn.unfold(xp, k, stride=s)                                     # [B, cin*k*k, L]  (extract_image_patches)
+            L_ = patches.shape[-1]
+            patches = patches.view(slots, cin, k * k, L_).permute(0, 3, 2, 1).reshape(slots, L_, k * k * cin)   # (ky,kx,ci) order
+            y = torch.baddbmm(view(2 * li + 1, 1, cout), patches, view(2 * li, k * k * cin, cout))             # batched matmul
+            h = int(round(L_ ** 0.5))
+            x = torch.relu(y).view(slots, h, h, cout).permute(0, 3, 1, 2)
+        f = x.permute(0, 2, 3, 1).reshape(slots, 1, 7744)
+        hdn = torch.relu(torch.baddbmm(view(7, 1, 512), f, view(6, 7744, 512)))
+        logits = torch.baddbmm(view(9, 1, 18), hdn, view(8, 512, 18))
+        return logits.argmax(dim=-1)
+
+    def generation():
+        for w0 in range(0, pop, slots):
+            n = min(slots, pop - w0)
+            for m in range(n):                                                       # models/base.py:158-192: one load per member
+                W[m].copy_(host[m & 7], non_blocking=True)
+            ret.zero_()
+            for t in range(T):
+                tick(t)
+                ret.add_(rew[t & 63])
+
+    for _ in range(args.warmup):
+        generation()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(0)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        generation()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop()
+    v = args.steps * pop * T / (ms / 1e3)
+    emit({"impl": "gpu-ref-proxy", "metric": "env-steps/sec across ES population (whole box)", "value": v, "unit": "env-steps/s",
+          "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+          "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+          "config": {"workload": f"frostbite_es_pop{pop}_LargeModel_T{T}", "population": pop, "env_slots_per_gpu": slots,
+                     "policy": "LargeModel (P=4052658, 18 actions)", "episode_len": T,
+                     "schedule": "reference GPU path proxy: materialised per-member weights, 4*P-byte H2D per member-episode, "
+                                 "5 cuBLAS batched matmuls per tick (torch.baddbmm), no update step"},
+          "clocks": clocks, "weights_streamed_per_tick_GB": slots * P * 4 / 1e9,
+          "note": "PROXY, not the reference (TensorFlow / gym_tensorflow / ALE absent): lower bound of the reference GPU "
+                  "schedule's time on this GPU; see bench_workloads.run_gpu_ref_proxy"})

@@ -387,7 +387,7 @@ conv_s2d_kernel(SlotArgs sa, int64_t off_w, LayerEpi epi, const void* __restrict
         constexpr float IN_SCALE = IN_U8 ? (1.0f / 255.0f) : 1.0f;
         constexpr int NJ = COUT / 16;
         const int act = epi.act;
-        const bool bn = epi.bn == DNE_BN_TF;
+        const bool bn = epi.bn != DNE_BN_NONE;
         uint32_t it = 0;
         for (int slot = blockIdx.x; slot < n_slots; slot += gridDim.x) {
             if (!slot_active(sa, slot)) continue;

@@ -308,7 +308,7 @@ static int forward_impl(dne_ctx* ctx, const dne_net_desc* net, const float* d_th
         return DNE_ERR_WS;
     }
     bool needs_vbn = false;
-    for (int l = 0; l < net->n_layers; ++l) needs_vbn = needs_vbn || (net->layers[l].bn == DNE_BN_TF);
+    for (int l = 0; l < net->n_layers; ++l) needs_vbn = needs_vbn || (net->layers[l].bn != DNE_BN_NONE);
     DNE_CHECK_ARG(!needs_vbn || d_vbn, "net has batch-norm layers: d_vbn (dne_vbn_reference_pass) required");
 
     // conv path: 2 = shifted-window kernels with TMA-fed images between the conv layers (conv_s2d.cu) when every conv

@@ -17,7 +17,7 @@ struct ChanEpi {
     int bn, act;
     __device__ __forceinline__ float apply(float acc) const {
         float y = acc + bias;
-        if (bn == DNE_BN_TF) y = (y - mean) * inv * gamma + beta;   // policies.py:322 (eps 1e-3, decay 0)
+        if (bn != DNE_BN_NONE) y = (y - mean) * inv * gamma + beta; // policies.py:322 (eps 1e-3, decay 0); batchnorm.py:85-93
         return apply_act(y, act);
     }
 };
@@ -28,12 +28,17 @@ __device__ __forceinline__ ChanEpi make_chan_epi(const SlotArgs& sa, const Layer
     c.act = e.act;
     c.bias = (e.off_b >= 0) ? perturbed(th[e.off_b + n], s, sa.noise[idx + e.off_b + n]) : 0.0f;
     c.mean = 0.f; c.inv = 1.f; c.gamma = 1.f; c.beta = 0.f;
-    if (e.bn == DNE_BN_TF) {
+    if (e.bn != DNE_BN_NONE) {
         const float* st = e.vbn + (int64_t)slot * e.vbn_len + e.bn_off;
         c.mean = st[n];
         c.inv = __fdiv_rn(1.0f, __fsqrt_rn(st[cout + n] + 1e-3f));
-        c.gamma = perturbed(th[e.off_gamma + n], s, sa.noise[idx + e.off_gamma + n]);
-        c.beta = perturbed(th[e.off_beta + n], s, sa.noise[idx + e.off_beta + n]);
+        if (e.bn == DNE_BN_TF) {
+            c.gamma = perturbed(th[e.off_gamma + n], s, sa.noise[idx + e.off_gamma + n]);
+            c.beta = perturbed(th[e.off_beta + n], s, sa.noise[idx + e.off_beta + n]);
+        } else {                           // DNE_BN_GPU: the layer has no bias; its 'b' is added after the normalisation
+            c.beta = c.bias;
+            c.bias = 0.0f;
+        }
     }
     return c;
 }

@@ -183,14 +183,20 @@ __device__ __forceinline__ void split_f16(float x, __half& h0, __half& h1) {
     h0 = __float2half_rn(fminf(fmaxf(x, -65504.0f), 65504.0f));
     h1 = __float2half_rn((x - __half2float(h0)) * F16_LO_SCALE);
 }
+// two values at a time with the packed conversions (cvt.rn.satfinite.f16x2.f32: saturating, one instruction per pair)
+__device__ __forceinline__ void split_f16x2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(x1), "f"(x0));      // d = {hi half: a, lo half: b}
+    const __half2 h = *reinterpret_cast<const __half2*>(&hi);
+    const float2 hf = __half22float2(h);
+    const float r0 = (x0 - hf.x) * F16_LO_SCALE, r1 = (x1 - hf.y) * F16_LO_SCALE;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(r1), "f"(r0));
+}
 // eight values -> one 16-byte row of the hi plane and one of the (scaled) lo plane
 __device__ __forceinline__ void split_f16x8(const float (&x)[8], uint4& hi, uint4& lo) {
-    __half h[8], l[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) split_f16(x[i], h[i], l[i]);
-    auto pk = [](__half a, __half b) { return (uint32_t)__half_as_ushort(a) | ((uint32_t)__half_as_ushort(b) << 16); };
-    hi = make_uint4(pk(h[0], h[1]), pk(h[2], h[3]), pk(h[4], h[5]), pk(h[6], h[7]));
-    lo = make_uint4(pk(l[0], l[1]), pk(l[2], l[3]), pk(l[4], l[5]), pk(l[6], l[7]));
+    split_f16x2(x[0], x[1], hi.x, lo.x);
+    split_f16x2(x[2], x[3], hi.y, lo.y);
+    split_f16x2(x[4], x[5], hi.z, lo.z);
+    split_f16x2(x[6], x[7], hi.w, lo.w);
 }
 __device__ __forceinline__ void sts128u(uint32_t saddr, const uint4& v) {
     asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");

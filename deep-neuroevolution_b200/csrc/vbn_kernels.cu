@@ -150,7 +150,8 @@ vbn_apply_kernel(SlotArgs sa, float* __restrict__ Y, int64_t y_slot_stride, int6
     for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < elems; e += (int64_t)gridDim.x * blockDim.x) {
         const int c = (int)(e % C);
         const float inv = __fdiv_rn(1.0f, __fsqrt_rn(st[C + c] + 1e-3f));
-        const float gamma = v_perturbed(th[off_gamma + c], s, sa.noise[idx + off_gamma + c]);
+        // off_gamma < 0: ModelVirtualBN flavour (batchnorm.py:85-93): no gamma, off_beta is the post-normalisation bias 'b'
+        const float gamma = off_gamma >= 0 ? v_perturbed(th[off_gamma + c], s, sa.noise[idx + off_gamma + c]) : 1.0f;
         const float beta = v_perturbed(th[off_beta + c], s, sa.noise[idx + off_beta + c]);
         y[e] = apply_act((y[e] - st[c]) * inv * gamma + beta, act);
     }
@@ -168,7 +169,7 @@ static int64_t v_layer_out_elems(const dne_layer_desc& L) {
 static int last_bn_layer(const dne_net_desc* net) {
     int last = -1;
     for (int l = 0; l < net->n_layers; ++l)
-        if (net->layers[l].bn == DNE_BN_TF) last = l;
+        if (net->layers[l].bn != DNE_BN_NONE) last = l;
     return last;
 }
 
@@ -221,7 +222,8 @@ extern "C" int dne_vbn_reference_pass(dne_ctx* ctx, const dne_net_desc* net, con
         off += align_up((size_t)n_slots * n_ref * oe * sizeof(float), 256);
         const int64_t out_slot_stride = (int64_t)n_ref * oe;
         LayerEpi epi;                      // raw pre-BN output: bias only
-        epi.off_b = L.off_b; epi.off_beta = -1; epi.off_gamma = -1;
+        const int64_t pre_b = (L.bn == DNE_BN_GPU) ? -1 : L.off_b;   // ModelVirtualBN layers have no pre-normalisation bias
+        epi.off_b = pre_b; epi.off_beta = -1; epi.off_gamma = -1;
         epi.act = DNE_ACT_NONE; epi.bn = DNE_BN_NONE; epi.bn_off = 0; epi.vbn_len = 0; epi.vbn = nullptr;
         if (L.kind == DNE_CONV) {
             DNE_CHECK_ARG((int64_t)L.hin * L.hin * L.cin == cur_elems, "conv layer input size mismatch");
@@ -236,7 +238,7 @@ extern "C" int dne_vbn_reference_pass(dne_ctx* ctx, const dne_net_desc* net, con
         } else {
             DNE_CHECK_ARG(!cur_u8 && L.cin == cur_elems && L.cin % 4 == 0, "dense layer input mismatch");
             dim3 grid((L.cout + MG_BN - 1) / MG_BN, (n_ref + MG_BM - 1) / MG_BM, n_slots);
-            member_gemm_kernel<<<grid, MG_THREADS, 0, st>>>(sa, L.off_w, L.off_b, (const float*)cur,
+            member_gemm_kernel<<<grid, MG_THREADS, 0, st>>>(sa, L.off_w, pre_b, (const float*)cur,
                                                            (int64_t)n_ref * cur_elems, n_ref, L.cin, L.cout, out,
                                                            out_slot_stride);
             DNE_LAUNCHED(1);
@@ -244,14 +246,15 @@ extern "C" int dne_vbn_reference_pass(dne_ctx* ctx, const dne_net_desc* net, con
         DNE_LAUNCH_CHECK();
         const int C = L.cout;
         const int rows = (int)(out_slot_stride / C);
-        if (L.bn == DNE_BN_TF) {
+        if (L.bn != DNE_BN_NONE) {
             vbn_stats_kernel<<<dim3((C + 31) / 32, n_slots), 256, 0, st>>>(sa, out, out_slot_stride, rows, C, d_vbn,
                                                                           net->vbn_len, L.bn_off);
             DNE_LAUNCH_CHECK1();
             if (l < last) {
                 const int gx = (int)((out_slot_stride + 255) / 256 < 1024 ? (out_slot_stride + 255) / 256 : 1024);
                 vbn_apply_kernel<<<dim3(gx, n_slots), 256, 0, st>>>(sa, out, out_slot_stride, out_slot_stride, C,
-                                                                   L.act, L.off_beta, L.off_gamma, d_vbn,
+                                                                   L.act, L.bn == DNE_BN_GPU ? L.off_b : L.off_beta,
+                                                                   L.bn == DNE_BN_GPU ? (int64_t)-1 : L.off_gamma, d_vbn,
                                                                    net->vbn_len, L.bn_off);
                 DNE_LAUNCH_CHECK1();
             }

@@ -17,7 +17,7 @@ LIB_PATH = os.environ.get("DNE_LIB") or os.path.join(_HERE, "libdne.so")     # D
 DNE_MAX_LAYERS = 8
 CONV, DENSE = 0, 1
 ACT_NONE, ACT_RELU, ACT_TANH = 0, 1, 2
-BN_NONE, BN_TF = 0, 1
+BN_NONE, BN_TF, BN_GPU = 0, 1, 2
 OB_ATARI_U8, OB_VECTOR = 0, 1
 
 

@@ -7,6 +7,7 @@ gpu path gpu_implementation/neuroevolution/models/base.py:165-192):
   Model          models/dqn.py:25-36      conv1[8,8,4,16] b conv2[4,4,16,32] b fc[3872,256] b out[256,A] b
   GAAtariPolicy  policies.py:449-459      same shapes as Model (name/w, name/b)
   ESAtariPolicy  policies.py:319-330      each BN'd layer: weights, biases, BatchNorm/beta, BatchNorm/gamma
+  ModelVirtualBN models/batchnorm.py:50-123  Model's layout; layers without bias, 'b' is added AFTER (x-mean)/sqrt(var+eps)
   MujocoPolicy   policies.py:155-162,195  l0..lN dense tanh, 'out' dense (continuous head)
 Kernels are HWIO, activations NHWC, flatten order (h, w, c); conv padding is TF 'SAME'.
 """
@@ -92,6 +93,7 @@ def _finish(net: NetSpec) -> NetSpec:
             off += l.cout
             l.off_gamma = off
             off += l.cout
+        if l.bn != F.BN_NONE:                    # (mean, var) per channel in the slot's virtual-batch-norm statistics
             l.bn_off = bn_off
             bn_off += 2 * l.cout
     net.num_params = off
@@ -134,6 +136,10 @@ def make_net(name: str, num_actions: int = 18, ob_dim: int = 376, hidden: Sequen
     if name == "ESAtariPolicy":
         layers = [_conv(4, 16, 8, 4, 84, bn=F.BN_TF), _conv(16, 32, 4, 2, 21, bn=F.BN_TF),
                   _dense(11 * 11 * 32, 256, bn=F.BN_TF), _dense(256, A, act=F.ACT_NONE)]
+        return _finish(NetSpec(name, layers, F.OB_ATARI_U8, 84 * 84 * 4))
+    if name == "ModelVirtualBN":                 # gpu_implementation/neuroevolution/models/batchnorm.py:50-123
+        layers = [_conv(4, 16, 8, 4, 84, bn=F.BN_GPU), _conv(16, 32, 4, 2, 21, bn=F.BN_GPU),
+                  _dense(11 * 11 * 32, 256, bn=F.BN_GPU), _dense(256, A, act=F.ACT_NONE, std=ac_init_std)]
         return _finish(NetSpec(name, layers, F.OB_ATARI_U8, 84 * 84 * 4))
     if name == "MujocoPolicy":
         act = {"tanh": F.ACT_TANH, "relu": F.ACT_RELU}[nonlin]

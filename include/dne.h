@@ -45,6 +45,8 @@ extern "C" {
 #define DNE_ACT_TANH 2
 #define DNE_BN_NONE 0
 #define DNE_BN_TF   1          /* contrib.layers.batch_norm(scale=True, decay=0, eps=1e-3): policies.py:322 */
+#define DNE_BN_GPU  2          /* ModelVirtualBN (gpu_implementation/neuroevolution/models/batchnorm.py:64-93): layer without
+                                  bias, (x - mean) / sqrt(var + 1e-3) + b, no gamma; off_b is that post-normalisation bias */
 
 /* observation kinds */
 #define DNE_OB_ATARI_U8 0      /* uint8 [slots,84,84,4], scaled by 1/255 (atari_wrappers.py:186) */

@@ -285,6 +285,13 @@ def make_net(name: str, num_actions: int = 18, ob_dim: int = 376, hidden=(256, 2
         layers = [conv(4, 16, 8, 4, 84, bn="tf"), conv(16, 32, 4, 2, 21, bn="tf"),
                   dense(11 * 11 * 32, 256, bn="tf"), dense(256, A, act="none")]
         return _finish(Net(name, layers, (84, 84, 4)))
+    if name == "ModelVirtualBN":
+        # gpu_implementation/neuroevolution/models/batchnorm.py:50-123: conv / dense WITHOUT bias, then
+        # (x - mean) * 1/sqrt(var + 1e-3) + b with a per-channel bias b created inside the BatchNorm scope (no gamma):
+        # creation order w, b per layer -- the same flat layout as Model, but 'b' acts AFTER the normalisation
+        layers = [conv(4, 16, 8, 4, 84, bn="vbn_gpu"), conv(16, 32, 4, 2, 21, bn="vbn_gpu"),
+                  dense(11 * 11 * 32, 256, bn="vbn_gpu"), dense(256, A, act="none", std=0.1)]
+        return _finish(Net(name, layers, (84, 84, 4)))
     if name == "MujocoPolicy":
         dims = [ob_dim] + list(hidden)
         layers = [dense(dims[i], dims[i + 1], act="tanh") for i in range(len(hidden))]
@@ -366,8 +373,19 @@ def forward(net: Net, theta: np.ndarray, obs: np.ndarray, *, vbn_stats=None, is_
             if x.ndim > 2:
                 x = x.reshape(x.shape[0], -1)       # flatten (h,w,c)  tf_util.py:284-285
             y = (torch.from_numpy(np.ascontiguousarray(x)) @ torch.from_numpy(np.ascontiguousarray(p["w"]))).numpy()
-        if l.bias:
+        if l.bias and l.bn != "vbn_gpu":
             y = y + p["b"].reshape((1,) * (y.ndim - 1) + (-1,))
+        if l.bn == "vbn_gpu":                     # batchnorm.py:64-93: moments over the batch / spatial axes, inv std stored
+            axes = tuple(range(y.ndim - 1))
+            if is_ref:
+                mean = y.mean(axis=axes, dtype=np.float64).astype(f32)
+                var = np.square(y.astype(np.float64) - mean.astype(np.float64)).mean(axis=axes).astype(f32)
+                stats_out.append((mean, var))
+            else:
+                mean, var = vbn_stats[bn_i]
+            bn_i += 1
+            inv = (f32(1.0) / np.sqrt(var + f32(BN_EPS))).astype(f32)
+            y = ((y - mean) * inv + p["b"]).astype(f32)
         if l.bn == "tf":
             axes = tuple(range(y.ndim - 1))
             if is_ref:

@@ -182,10 +182,13 @@ def test_largemodel_four_tables_phase_events_match_one_table(ctx, host_noise):
         assert torch.equal(torch.cat([t.actions for t in tabs])[decided], ref_actions[decided])
 
 
-def test_es_atari_policy_vbn_at_config_size(ctx, host_noise):
+@pytest.mark.parametrize("name", ["ESAtariPolicy", "ModelVirtualBN"])
+def test_es_atari_policy_vbn_at_config_size(ctx, host_noise, name):
     """frostbite_es.json: ESAtariPolicy with the 128-observation reference batch (es.py:105-113,160-162).  The
-    reference pass at n_ref = 128 and the act path on its statistics, 8 slots vs the oracle."""
-    net, net_o = N.make_net("ESAtariPolicy"), O.make_net("ESAtariPolicy")
+    reference pass at n_ref = 128 and the act path on its statistics, 8 slots vs the oracle.  ModelVirtualBN is the
+    GPU path's flavour (gpu_implementation/neuroevolution/models/batchnorm.py:50-123): no layer bias, no gamma,
+    (x - mean) / sqrt(var + 1e-3) + b."""
+    net, net_o = N.make_net(name), O.make_net(name)
     P = net.num_params
     rs = np.random.RandomState(2121)
     theta = (rs.randn(P) * 0.05).astype(np.float32)

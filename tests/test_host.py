@@ -58,7 +58,7 @@ def test_ws_queries_run_without_gpu():
         assert 0 < nb.value < 4 << 30
 
 
-@pytest.mark.parametrize("name", ["LargeModel", "Model", "GAAtariPolicy", "ESAtariPolicy", "MujocoPolicy"])
+@pytest.mark.parametrize("name", ["LargeModel", "Model", "GAAtariPolicy", "ESAtariPolicy", "MujocoPolicy", "ModelVirtualBN"])
 def test_layouts_match_oracle(name):
     from dne import _ffi as F, nets
     net, ref = nets.make_net(name), O.make_net(name)
@@ -71,7 +71,7 @@ def test_layouts_match_oracle(name):
             assert (l.hout, l.pad) == (lo.hout, lo.pad_before)
     d = net.desc
     assert d.num_params == net.num_params and d.n_layers == len(net.layers)
-    assert d.vbn_len == sum(2 * l.cout for l in net.layers if l.bn == F.BN_TF)
+    assert d.vbn_len == sum(2 * l.cout for l in net.layers if l.bn != F.BN_NONE)
 
 
 def test_synthetic_envs():
