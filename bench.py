@@ -323,7 +323,7 @@ def run_b200(args):
     achieved = alg_bytes / (avg_ms * 1e-3) / 1e9 if n_timed else None
     traffic = None
     try:      # DRAM bytes of the same kernel from the committed ncu --set full capture, scaled to this run's pairs/launch
-        with open(os.path.join(ROOT, "profiles", "r01_ncu_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r02_ncu_traffic.json")) as f:
             tj = json.load(f)["gemv_bulk_kernel"]
         traffic = tj["dram_bytes_per_launch"] * pairs_per_launch / tj["pairs_per_launch"]
     except Exception:

@@ -254,7 +254,10 @@ int dne_launch_gemv_bulk(const SlotArgs& sa, const GemvSrc& src, int G, const fl
     const int n_items = n_groups * n_chunks;
     int grid = g_dne_gemv_ctas_per_sm * sm_count;   // 1 CTA/SM leaves room for the other stream's conv CTAs to co-reside
     if (grid > n_items) grid = n_items;
-    static bool attr_done[3] = {false, false, false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    static bool attr_done_dev[64][3] = {};                        // per device: one process may drive several GPUs
+    bool* attr_done = attr_done_dev[dev < 64 ? dev : 63];
     if (G == 2) {
         if (!attr_done[2]) {
             cudaFuncSetAttribute(gemv_bulk_kernel<2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);

@@ -300,7 +300,10 @@ static int launch_conv_tc(const SlotArgs& sa, const dne_layer_desc& L, const Lay
                           int64_t out_img_stride, int n_slots, int n_img, cudaStream_t st) {
     using Cfg = TcConvCfg<CIN, COUT, KS, STRIDE, HIN, HOUT, PAD, IN_U8, MTC, KC>;
     auto kern = conv_tc_kernel<CIN, COUT, KS, STRIDE, HIN, HOUT, PAD, IN_U8, MTC, KC>;
-    static bool attr_done = false;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    static bool attr_done_dev[64] = {};                           // per device
+    bool& attr_done = attr_done_dev[dev < 64 ? dev : 63];
     if (!attr_done) {
         cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES) != cudaSuccess)
@@ -462,7 +465,10 @@ theta_gemm_tc_kernel(const float* __restrict__ X, int M, int K, int N, const flo
 int dne_launch_theta_gemm_tc(const float* X, int M, int K, int N, const float* W, int k_per_split, int n_split,
                              float* part, cudaStream_t st) {
     if (K % 4 != 0 || N % 4 != 0 || k_per_split % TG_KC != 0) return DNE_ERR_UNSUP;
-    static bool attr_done = false;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    static bool attr_done_dev[64] = {};
+    bool& attr_done = attr_done_dev[dev < 64 ? dev : 63];
     if (!attr_done) {
         cudaFuncSetAttribute(theta_gemm_tc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         if (cudaFuncSetAttribute(theta_gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TG_SMEM_BYTES) != cudaSuccess)

@@ -92,8 +92,14 @@ def run_master(master_redis_cfg, log_dir, exp, *, max_iterations=None, n_slots=2
     P = policy.num_params
     dev = policy.device
     tslimit, incr_thr, incr_ratio, _, adaptive = _cutoff(config)
-    population_size = exp['population_size']          # ga.py:66
-    num_elites = exp['num_elites']                     # ga.py:67
+    # two selection schemes: the CPU driver's (ga.py:135-158: num_elites + top population_size) and, when the experiment
+    # carries the GPU path's keys (configurations/ga_atari_config.json: selection_threshold, validation_threshold,
+    # num_validation_episodes), Deep GA with a validation stage (gpu_implementation/ga.py:180-204,260-271)
+    deep = 'validation_threshold' in exp
+    population_size = exp['selection_threshold'] if deep else exp['population_size']          # ga.py:66
+    num_elites = 0 if deep else exp['num_elites']                                              # ga.py:67
+    elite = None
+    deep_stats, deep_extra = {}, {}
     cache = GenomeCache(ctx, policy.net, config.noise_stdev, exp.get('ga_mode', 'cpu'))
     runner = RolloutRunner(ctx, policy.net, env, n_slots=n_slots, group=1, pipeline=2 if n_slots % 2 == 0 else 1)
     population, population_score = [], np.array([], dtype=np.float32)
@@ -108,8 +114,10 @@ def run_master(master_redis_cfg, log_dir, exp, *, max_iterations=None, n_slots=2
         genomes, rets, lens = [], [], []
         num_eps = num_ts = 0
         first = True
-        while first or num_eps < config.episodes_per_batch or num_ts < config.timesteps_per_batch:   # ga.py:94
-            n_off = config.episodes_per_batch if first else world * n_slots
+        while first or (not deep and (num_eps < config.episodes_per_batch or num_ts < config.timesteps_per_batch)):   # ga.py:94
+            # offspring per generation: the CPU driver's episode quota (ga.py:94), or exactly population_size on the
+            # GPU path (gpu_implementation/ga.py:165-166)
+            n_off = (exp['population_size'] if deep else config.episodes_per_batch) if first else world * n_slots
             parents = [int(rs.randint(len(population))) if len(population) > 0 else -1 for _ in range(n_off)]   # ga.py:251-254
             new_seeds = [noise.sample_index(rs, P) for _ in range(n_off)]
             batch = [(tuple(population[p]) if p >= 0 else ()) + (s,) for p, s in zip(parents, new_seeds)]
@@ -143,19 +151,65 @@ def run_master(master_redis_cfg, log_dir, exp, *, max_iterations=None, n_slots=2
         episodes_so_far += len(returns)
         timesteps_so_far += int(lengths_n2.sum())
 
-        # ---- selection (ga.py:135-149): elites first, then this generation's offspring ----
-        cand = [tuple(g) for g in population[:num_elites]] + genomes
-        fit = np.concatenate([population_score[:num_elites], returns]).astype(np.float32)
-        T = min(population_size, len(cand))
-        d_fit = torch.from_numpy(fit).to(dev)
-        sel = torch.empty(T, dtype=torch.int32, device=dev)
-        F.check(F.lib().dne_ga_truncate(F.ptr(d_fit), len(fit), T, F.ptr(sel), F.stream_ptr()))
-        sel = sel.cpu().numpy()
-        population = [cand[i] for i in sel]
-        population_score = fit[sel]
-        assert len(population) == T and np.max(fit) == population_score[0]            # ga.py:148-149
-        cache.rebuild(population)                                                     # parents for the next generation
-        policy.set_trainable_flat(cache.theta[0])                                     # elite (ga.py:151-158)
+        if deep:
+            # ---- Deep GA of the GPU path (gpu_implementation/ga.py:180-204,260-271): stable descending sort, the top
+            # validation_threshold (+ last elite) re-evaluated num_validation_episodes times, elite = argmax of the mean
+            # validation return, parents = top selection_threshold with the elite forced in ----
+            d_fit = torch.from_numpy(returns.astype(np.float32)).to(dev)
+            order_t = torch.empty(len(returns), dtype=torch.int32, device=dev)
+            F.check(F.lib().dne_ga_truncate(F.ptr(d_fit), len(returns), len(returns), F.ptr(order_t), F.stream_ptr()))   # ga.py:180
+            order = order_t.cpu().numpy()
+            pop_sorted = [tuple(genomes[i]) for i in order]
+            V, n_val = int(exp['validation_threshold']), int(exp['num_validation_episodes'])
+            val_pop = pop_sorted[:V]
+            if elite is not None:
+                val_pop = [elite] + val_pop[:-1]                                            # ga.py:186-188
+            val_theta = torch.empty(len(val_pop), P, dtype=torch.float32, device=dev)
+            index = {sd: i for i, sd in enumerate(cache.seeds)}
+            for j, gnm in enumerate(val_pop):                                               # compute_weights_from_seeds(cache=parents)
+                if gnm in index:
+                    val_theta[j].copy_(cache.theta[index[gnm]])
+                elif len(gnm) > 1 and gnm[:-1] in index:
+                    F.check(F.lib().dne_ga_mutate(ctx.handle, F.ptr(cache.theta[index[gnm[:-1]]]), int(gnm[-1]), cache.sigma, P,
+                                                  F.ptr(val_theta[j]), F.stream_ptr()))
+                else:
+                    cache.materialize(gnm, val_theta[j])
+            v_units = [Unit(0, (0.0,), j) for j in range(len(val_pop)) for _ in range(n_val)]
+            vlo, vhi = shard.shard_bounds(len(v_units), rank, world)
+            vres = runner.run(val_theta, v_units[vlo:vhi], tslimit)
+            vpack = torch.from_numpy(np.stack([vres.returns[:, 0], vres.lengths[:, 0].astype(np.float32)], axis=1)).to(dev)
+            vall = shard.all_gather_rows(vpack, len(v_units)).cpu().numpy()
+            val_returns = vall[:, 0].reshape(len(val_pop), n_val)
+            val_means = val_returns.mean(axis=1)
+            elite_idx = int(np.argmax(val_means))                                           # ga.py:197
+            elite = val_pop[elite_idx]
+            Tsel = int(exp['selection_threshold'])
+            top = pop_sorted[:Tsel]
+            population = top if elite in top else [elite] + top[:Tsel - 1]                  # ga.py:260-271
+            score_of = {tuple(genomes[i]): float(returns[i]) for i in order[::-1]}
+            population_score = np.array([score_of.get(g, float(val_means[elite_idx])) for g in population], dtype=np.float32)
+            timesteps_so_far += int(vall[:, 1].sum())
+            cache.rebuild(population)
+            policy.set_trainable_flat(cache.theta[population.index(elite)])
+            deep_stats = dict(TruncatedPopulationRewMean=float(np.mean([score_of.get(g, np.nan) for g in val_pop])),
+                              TruncatedPopulationValidationRewMean=float(val_means.mean()),
+                              TruncatedPopulationEliteValidationRewMean=float(val_means.max()),
+                              TruncatedPopulationEliteIndex=elite_idx, ValidationTimestepsThisIter=int(vall[:, 1].sum()))
+            deep_extra = dict(val_pop=val_pop, val_returns=val_returns, elite=elite, pop_sorted=pop_sorted)
+        if not deep:
+            # ---- selection (ga.py:135-149): elites first, then this generation's offspring ----
+            cand = [tuple(g) for g in population[:num_elites]] + genomes
+            fit = np.concatenate([population_score[:num_elites], returns]).astype(np.float32)
+            T = min(population_size, len(cand))
+            d_fit = torch.from_numpy(fit).to(dev)
+            sel = torch.empty(T, dtype=torch.int32, device=dev)
+            F.check(F.lib().dne_ga_truncate(F.ptr(d_fit), len(fit), T, F.ptr(sel), F.stream_ptr()))
+            sel = sel.cpu().numpy()
+            population = [cand[i] for i in sel]
+            population_score = fit[sel]
+            assert len(population) == T and np.max(fit) == population_score[0]            # ga.py:148-149
+            cache.rebuild(population)                                                     # parents for the next generation
+            policy.set_trainable_flat(cache.theta[0])                                     # elite (ga.py:151-158)
 
         if adaptive and (lengths_n2 == tslimit).mean() >= incr_thr:                   # ga.py:161-164
             tslimit = int(incr_ratio * tslimit)
@@ -165,14 +219,16 @@ def run_master(master_redis_cfg, log_dir, exp, *, max_iterations=None, n_slots=2
                      EpisodesThisIter=int(lengths_n2.size), EpisodesSoFar=int(episodes_so_far),
                      TimestepsThisIter=int(lengths_n2.sum()), TimestepsSoFar=int(timesteps_so_far),
                      UniqueWorkers=world, TimeElapsedThisIter=step_tend - step_tstart, TimeElapsed=step_tend - tstart)
+        stats.update(deep_stats)
         if rank == 0:
-            tlogger.log('Elite: {} score: {}'.format(population[0], population_score[0]))
+            tlogger.log('Elite: {} score: {}'.format(elite if deep else population[0], population_score[0]))
             for k, v in stats.items():
                 tlogger.record_tabular(k, v)
             tlogger.dump_tabular()
         if on_iteration is not None:
             on_iteration(it, stats, dict(population=population, population_score=population_score, returns=returns,
-                                         genomes=genomes, elite_theta=cache.theta[0]))
+                                         genomes=genomes, elite_theta=cache.theta[population.index(elite)] if deep else cache.theta[0],
+                                         **deep_extra))
         if rank == 0 and log_dir and config.snapshot_freq != 0:                        # ga.py:198-206 (every iteration)
             import os.path as osp
             policy.save(osp.join(log_dir, 'snapshot_iter{:05d}_rew{}.h5'.format(it, int(population_score[0]))))

@@ -486,6 +486,30 @@ def ga_truncate(fitness: np.ndarray, T: int) -> np.ndarray:
     return order[:T].astype(np.int32)
 
 
+def deep_ga_validation_population(population_sorted, elite, validation_threshold: int):
+    """gpu_implementation/ga.py:185-188: the top ``validation_threshold`` individuals of the fitness-sorted population,
+    with last generation's elite put first (dropping the last of them)."""
+    val = list(population_sorted[:validation_threshold])
+    if elite is not None:
+        val = [elite] + val[:-1]
+    return val
+
+
+def deep_ga_elite(validation_population, validation_returns):
+    """gpu_implementation/ga.py:191-198: mean validation return per candidate; elite = argmax (first maximum)."""
+    means = [float(np.mean(r)) for r in validation_returns]
+    return validation_population[int(np.argmax(means))], means
+
+
+def deep_ga_parents(population_sorted, elite, selection_threshold: int):
+    """gpu_implementation/ga.py:260-271: the top ``selection_threshold`` individuals; if the elite is not among them it
+    takes the first place and the last of them is dropped."""
+    top = list(population_sorted[:selection_threshold])
+    if elite in top:
+        return top
+    return [elite] + top[:selection_threshold - 1]
+
+
 # --------------------------------------------------------------------------------------------------
 # a-12  novelty                                              es_distributed/nses.py:12-32,226-228
 # --------------------------------------------------------------------------------------------------

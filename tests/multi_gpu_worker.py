@@ -43,7 +43,7 @@ def main():
     def on_it(it, stats, extra):
         if algo == "es":
             rec[f"returns_{it}"], rec[f"idx_{it}"] = extra["returns_n2"].copy(), extra["noise_inds_n"].copy()
-            rec[f"theta_{it}"] = extra["theta"].cpu().numpy()
+            rec[f"theta_{it}"], rec[f"g_{it}"] = extra["theta"].cpu().numpy(), extra["g"].cpu().numpy()
         elif algo == "ga":
             rec[f"returns_{it}"] = np.asarray(extra["returns"]).copy()
             rec[f"score_{it}"] = np.asarray(extra["population_score"]).copy()
@@ -52,6 +52,7 @@ def main():
         else:
             rec[f"returns_{it}"], rec[f"novelty_{it}"] = extra["returns_n2"].copy(), extra["novelty_n2"].copy()
             rec[f"theta_{it}"], rec[f"parent_{it}"] = extra["theta"].cpu().numpy(), np.int64(extra["parent"])
+            rec[f"g_{it}"] = extra["g"].cpu().numpy()
             rec[f"archive_len_{it}"] = np.int64(len(extra["archive"]))
             rec[f"archive_last_{it}"] = extra["archive"].seqs[-1].copy()
     if algo == "es":

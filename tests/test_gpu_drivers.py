@@ -254,3 +254,41 @@ def test_es_humanoid_ob_stat_plumbing_matches_running_stat(noise, tmp_path):
         np.testing.assert_allclose(s_sumsq, orc.sumsq, rtol=1e-5, atol=1e-4)
         np.testing.assert_allclose(s_mean, orc.mean, rtol=1e-4, atol=1e-5)
         np.testing.assert_allclose(s_std, orc.std, rtol=1e-4, atol=1e-5)
+
+
+def test_deep_ga_validation_and_elite_selection(noise, host_noise, tmp_path):
+    """gpu_implementation/ga.py:180-204,260-271 (configurations/ga_atari_config.json keys): fitness-sorted population, the top
+    validation_threshold (+ last elite) re-evaluated num_validation_episodes times, elite = argmax of the mean validation
+    return, parents = top selection_threshold with the elite forced in -- every step re-derived by the oracle from the
+    returns the driver reports."""
+    from es_distributed import ga as GA
+    from es_distributed import es as ES
+    exp = {"config": {"calc_obstat_prob": 0.0, "episodes_per_batch": 12, "eval_prob": 0.0, "l2coeff": 0.005, "noise_stdev": 0.002,
+                      "snapshot_freq": 0, "timesteps_per_batch": 10, "return_proc_mode": "centered_rank", "episode_cutoff_mode": 5000},
+           "env_id": "FrostbiteNoFrameskip-v4", "ga_mode": "gpu", "policy": {"args": {}, "type": "GAAtariPolicy"},
+           "population_size": 12, "selection_threshold": 4, "validation_threshold": 3, "num_validation_episodes": 5,
+           "num_test_episodes": 2, "mutation_power": 0.002}
+    env = SyntheticAtariEnv(8, episode_len=(3, 9), seed=5)
+    log = []
+    ES.set_default_noise(noise)
+    GA.run_master(None, str(tmp_path), json.loads(json.dumps(exp)), max_iterations=3, n_slots=8, env=env, noise=noise, seed=3,
+                  on_iteration=lambda it, stats, extra: log.append((it, dict(stats), extra)))
+    assert len(log) == 3
+    elite = None
+    for it, stats, ex in log:
+        fit = np.asarray(ex["returns"], dtype=np.float32)
+        genomes = [tuple(g) for g in ex["genomes"]]
+        assert len(genomes) == 12
+        order = O.ga_truncate(fit, len(fit))                                    # stable descending (ga.py:180)
+        pop_sorted = [genomes[i] for i in order]
+        assert pop_sorted == ex["pop_sorted"]
+        val_pop = O.deep_ga_validation_population(pop_sorted, elite, 3)
+        assert val_pop == ex["val_pop"]
+        assert ex["val_returns"].shape == (3, 5)
+        new_elite, means = O.deep_ga_elite(val_pop, list(ex["val_returns"]))
+        assert new_elite == ex["elite"] and stats["TruncatedPopulationEliteIndex"] == int(np.argmax(means))
+        parents = O.deep_ga_parents(pop_sorted, new_elite, 4)
+        assert parents == [tuple(g) for g in ex["population"]]
+        assert new_elite in parents and len(parents) == 4
+        assert all(1 <= len(g) <= it for g in genomes)                            # offspring = one mutation of a cached parent
+        elite = new_elite

@@ -37,16 +37,26 @@ def test_world2_matches_world1(algo, tmp_path):
     two = _run(algo, 2, str(tmp_path / "w2.npz"), 29511 + ["es", "ga", "nsr"].index(algo))
     assert int(one["world"]) == 1 and int(two["world"]) == 2
     assert set(one.files) == set(two.files)
-    for key in one.files:
+    bad = []
+    for key in sorted(one.files):
         if key == "world":
             continue
         a, b = one[key], two[key]
-        if key.startswith(("theta_", "elite_")):
+        if key.startswith("g_"):
+            # the all_reduce adds the per-rank partial gradients in another order than one rank's single sum
+            ok = np.abs(a - b).max() <= 1e-5 * np.abs(a).max()
+        elif key.startswith(("theta_", "elite_")):
             if algo == "ga":
-                np.testing.assert_array_equal(a, b)          # seed chains rebuilt identically on every rank: bit-exact
+                ok = np.array_equal(a, b)                    # seed chains rebuilt identically on every rank: bit-exact
             else:
-                assert np.abs(a - b).max() <= 1e-5 * np.abs(a).max(), key
+                # Adam's step is lr * m / (sqrt(v) + eps): where |g_i| is within rounding of zero the step itself moves by up
+                # to a fraction of lr (0.01), everywhere else by nothing -- bound the size and the number of such coordinates
+                d = np.abs(a - b)
+                ok = d.max() <= 1e-2 * 0.01 and (d > 1e-6).mean() < 1e-3
         elif key.startswith("novelty_"):
-            np.testing.assert_allclose(a, b, rtol=1e-6, err_msg=key)   # after the first update theta differs by ~1e-7 relative
+            ok = np.allclose(a, b, rtol=1e-6, atol=0)
         else:
-            np.testing.assert_array_equal(a, b, err_msg=key)  # returns, indices, scores, populations, archive, parent
+            ok = np.array_equal(a, b)                        # returns, indices, scores, populations, archive, parent
+        if not ok:
+            bad.append(key)
+    assert not bad, bad

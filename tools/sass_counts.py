@@ -1,0 +1,48 @@
+"""Regenerate profiles/r02_sass_counts.md: per-kernel counts of the Blackwell-specific SASS mnemonics in libdne.so
+(cuobjdump -sass; runs on the CPU build box).  B200_PROFILING.md: tcgen05.mma -> UTC*MMA, tcgen05.ld -> LDTM,
+cp.async.bulk -> UBLKCP, TMA tensor loads -> UTMALDG, legacy mma.sync -> HMMA."""
+import collections
+import os
+import re
+import subprocess
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LIB = os.path.join(ROOT, "deep-neuroevolution_b200", "dne", "libdne.so")
+txt = subprocess.run(["cuobjdump", "-sass", LIB], capture_output=True, text=True).stdout
+pat = {"UTCHMMA": r"\bUTCHMMA\b", "UTCBAR": r"\bUTCBAR\b", "LDTM": r"\bLDTM\b", "UBLKCP": r"\bUBLKCP\b", "UBLKPF": r"\bUBLKPF\b",
+       "UTMALDG": r"\bUTMALDG\b", "SYNCS": r"\bSYNCS\b", "HMMA": r"\bHMMA\b", "F2FP": r"\bF2FP\b"}
+rows = []
+for p in re.split(r"\n\s*Function : ", txt)[1:]:
+    name = p.split("\n", 1)[0].strip()
+    try:
+        name = subprocess.run(["c++filt", name], capture_output=True, text=True).stdout.strip() or name
+    except OSError:
+        pass
+    rows.append((name, len(re.findall(r"/\*[0-9a-f]{4}\*/", p)), {k: len(re.findall(v, p)) for k, v in pat.items()}))
+out = ["# r02 SASS evidence (`cuobjdump -sass deep-neuroevolution_b200/dne/libdne.so`, sm_100a)", "",
+       "Per-kernel counts of the Blackwell-specific mnemonics (B200_PROFILING.md: `tcgen05.mma` -> `UTC*MMA`, `tcgen05.commit` ->",
+       "`UTCBAR`, `tcgen05.ld` -> `LDTM`, `cp.async.bulk` -> `UBLKCP`, mbarrier -> `SYNCS`, packed fp16 convert -> `F2FP`).",
+       "Regenerate: `python tools/sass_counts.py`.", "", "| kernel | SASS instr | " + " | ".join(pat) + " |",
+       "|---|---|" + "---|" * len(pat)]
+tot = collections.Counter()
+for name, n, cnt in sorted(rows, key=lambda r: -(r[2]["UTCHMMA"] * 1000 + r[2]["UBLKCP"])):
+    if not any(cnt[k] for k in ("UTCHMMA", "LDTM", "UBLKCP", "UBLKPF", "UTMALDG", "HMMA")):
+        continue
+    short = name.replace("(anonymous namespace)::", "").replace("void ", "")
+    short = re.sub(r">\(.*$", ">", short) if ">(" in short else re.sub(r"\(.*$", "", short)
+    out.append(f"| `{short[:100]}` | {n} | " + " | ".join(str(cnt[k]) for k in pat) + " |")
+    tot.update(cnt)
+out.append("| **total** | | " + " | ".join(str(tot[k]) for k in pat) + " |")
+out += ["",
+        "* `conv_s2d_kernel<CIN, COUT, KS, S, HIN, HOUT, PAD, IN_U8>`: shifted-window implicit-GEMM convolutions (kind::f16 on 2 x fp16 "
+        "splits), A image and raw weight rows by `cp.async.bulk` (UBLKCP), accumulators in TMEM (LDTM in the epilogue warps).",
+        "* `theta_gemm_tma_kernel<MT, CL>`: pure TMA + tcgen05 GEMM, no staging threads; CL > 1 is the cluster-multicast variant "
+        "(measured slower, off by default).",
+        "* `gemv_bulk_kernel<G>`: the HBM-bound noise GEMV, cp.async.bulk ring (the dominant kernel of the tick).",
+        "* `conv_tc_kernel` / `theta_gemm_tc_kernel`: the r01 thread-staged tcgen05 kernels (kind::tf32), kept for A/B "
+        "(`dne_set_option(\"conv_tc\", 1)`) and used by the virtual-batch-norm reference pass.",
+        "* `UTMALDG` = 0 by design: every TMA transfer on this path is one contiguous run (images, weight rows and GEMM operands are "
+        "laid out for that), so the descriptor-less bulk form is what the data layout calls for.  `HMMA` = 0: no legacy "
+        "mma.sync / wmma anywhere."]
+open(os.path.join(ROOT, "profiles", "r02_sass_counts.md"), "w").write("\n".join(out) + "\n")
+print("\n".join(out[6:14]))
