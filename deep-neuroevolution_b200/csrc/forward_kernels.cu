@@ -448,8 +448,8 @@ dense_small_kernel(SlotArgs sa, int64_t off_w, LayerEpi epi, const float* __rest
 // shared memory and fed straight to the head (512x18 / 256x18 / 256x17) and its argmax -- one launch and one global round
 // trip less per tick.  Both phases are latency bound (L2 partials; theta + noise rows of the head), so every thread keeps 8
 // independent loads in flight and adds them in index order (the sums are order-deterministic).
-constexpr int DCH_MAXK = 1024, DCH_THREADS = 512, DCH_B = 8;
-__global__ void __launch_bounds__(DCH_THREADS)
+constexpr int DCH_MAXK = 1024, DCH_THREADS = 512, DCH_B = 8, DCH_HR = 20;
+__global__ void __launch_bounds__(DCH_THREADS, 2)
 dense_combine_head_kernel(SlotArgs sa, LayerEpi epi1, int n_slots, int N1, int G, const float* __restrict__ part_theta,
                           int n_split, int Gt, const float* __restrict__ part_noise, int n_chunks,
                           float* __restrict__ hidden_out, int64_t hidden_stride,
@@ -464,64 +464,82 @@ dense_combine_head_kernel(SlotArgs sa, LayerEpi epi1, int n_slots, int N1, int G
     const float* th = slot_theta(sa, slot);
     const int64_t idx = sa.noise_idx[slot];
     const float s = sa.scale[slot];
+    // The head's weights do not depend on phase 1: when a thread's share of rows fits in registers (K / RG <= DCH_HR), its
+    // theta / noise loads (HBM latency) are issued FIRST and overlap the L2 round trips of the partial sums below.
+    const int K = N1, N = N2;
+    const int RG = DCH_THREADS / N;
+    const int hn_ = t % N, rg = t / N;
+    const float* tw = th + off_w2;
+    const float* nz = sa.noise + idx + off_w2;
+    const int rows_pt = (K + RG - 1) / RG;
+    const bool pre = rows_pt <= DCH_HR;
+    float hw[DCH_HR], hz[DCH_HR];
+    if (pre && rg < RG) {
+#pragma unroll
+        for (int j = 0; j < DCH_HR; ++j) {
+            const int k = rg + j * RG;
+            const int64_t f = (int64_t)k * N + hn_;
+            hw[j] = k < K ? tw[f] : 0.0f;
+            hz[j] = k < K ? nz[f] : 0.0f;
+        }
+    }
     // ---- phase 1: y = act(bn(sum_split Ytheta + s * sum_chunk Ynoise + bias))  (dense_combine_kernel) ----
+    // partial sums: DCH_B predicated loads in flight, added in index order (same order as a sequential loop)
+    auto sum_strided = [](const float* p, int64_t stride, int count) {
+        float acc = 0.0f;
+        for (int c = 0; c < count; c += DCH_B) {
+            float v[DCH_B];
+#pragma unroll
+            for (int j = 0; j < DCH_B; ++j) v[j] = (c + j < count) ? p[(int64_t)(c + j) * stride] : 0.0f;
+#pragma unroll
+            for (int j = 0; j < DCH_B; ++j)
+                if (c + j < count) acc += v[j];
+        }
+        return acc;
+    };
     for (int n = t; n < N1; n += DCH_THREADS) {
+        const ChanEpi ce = make_chan_epi(sa, epi1, slot, N1, n, th, idx, s);      // its two loads go out before the partials
         const float* pt;
         int64_t pt_stride;
         if (Gt == 0) { pt = part_theta + (int64_t)slot * N1 + n; pt_stride = (int64_t)n_slots * N1; }
         else { pt = part_theta + (((int64_t)(slot / Gt) * n_split) * Gt + (slot % Gt)) * N1 + n; pt_stride = (int64_t)Gt * N1; }
-        float yt = 0.0f;
-        int c = 0;
-        for (; c + DCH_B <= n_split; c += DCH_B) {
-            float p[DCH_B];
-#pragma unroll
-            for (int j = 0; j < DCH_B; ++j) p[j] = pt[(int64_t)(c + j) * pt_stride];
-#pragma unroll
-            for (int j = 0; j < DCH_B; ++j) yt += p[j];
-        }
-        for (; c < n_split; ++c) yt += pt[(int64_t)c * pt_stride];
         const int group = slot / G, g = slot % G;
         const float* pn = part_noise + (((int64_t)group * n_chunks) * G + g) * N1 + n;
-        const int64_t pn_stride = (int64_t)G * N1;
-        float yn = 0.0f;
-        for (c = 0; c + DCH_B <= n_chunks; c += DCH_B) {
-            float p[DCH_B];
-#pragma unroll
-            for (int j = 0; j < DCH_B; ++j) p[j] = pn[(int64_t)(c + j) * pn_stride];
-#pragma unroll
-            for (int j = 0; j < DCH_B; ++j) yn += p[j];
-        }
-        for (; c < n_chunks; ++c) yn += pn[(int64_t)c * pn_stride];
-        const ChanEpi ce = make_chan_epi(sa, epi1, slot, N1, n, th, idx, s);
+        const float yt = sum_strided(pt, pt_stride, n_split);
+        const float yn = sum_strided(pn, (int64_t)G * N1, n_chunks);
         const float y = ce.apply(fmaf(s, yn, yt));
         xs[n] = y;
         if (hidden_out) hidden_out[(int64_t)slot * hidden_stride + n] = y;
     }
     __syncthreads();
-    // ---- phase 2: the head on x = xs.  Thread t < RG*N owns output column n = t % N and row group rg = t / N; one batch
-    // covers DCH_B*RG consecutive rows = contiguous weights, so the theta / noise loads are flat and coalesced ----
-    const int K = N1, N = N2;
-    const int RG = DCH_THREADS / N;
-    const int n = t % N, rg = t / N;
-    const float* tw = th + off_w2;
-    const float* nz = sa.noise + idx + off_w2;
+    // ---- phase 2: the head on x = xs.  Thread t < RG*N owns output column n = t % N and row group rg = t / N (rows rg,
+    // rg + RG, ...: a batch of rows is a contiguous run of weights, so the loads are flat and coalesced) ----
+    const int n = hn_;
     float acc = 0.0f;
     if (rg < RG) {
-        int k = rg;
-        for (; k + (DCH_B - 1) * RG < K; k += DCH_B * RG) {
-            float a[DCH_B], b[DCH_B];
+        if (pre) {
 #pragma unroll
-            for (int j = 0; j < DCH_B; ++j) {
-                const int64_t f = (int64_t)(k + j * RG) * N + n;
-                a[j] = tw[f];
-                b[j] = nz[f];
+            for (int j = 0; j < DCH_HR; ++j) {
+                const int k = rg + j * RG;
+                if (k < K) acc = fmaf(xs[k], perturbed(hw[j], s, hz[j]), acc);
             }
+        } else {
+            int k = rg;
+            for (; k + (DCH_B - 1) * RG < K; k += DCH_B * RG) {
+                float a[DCH_B], b[DCH_B];
 #pragma unroll
-            for (int j = 0; j < DCH_B; ++j) acc = fmaf(xs[k + j * RG], perturbed(a[j], s, b[j]), acc);
-        }
-        for (; k < K; k += RG) {
-            const int64_t f = (int64_t)k * N + n;
-            acc = fmaf(xs[k], perturbed(tw[f], s, nz[f]), acc);
+                for (int j = 0; j < DCH_B; ++j) {
+                    const int64_t f = (int64_t)(k + j * RG) * N + n;
+                    a[j] = tw[f];
+                    b[j] = nz[f];
+                }
+#pragma unroll
+                for (int j = 0; j < DCH_B; ++j) acc = fmaf(xs[k + j * RG], perturbed(a[j], s, b[j]), acc);
+            }
+            for (; k < K; k += RG) {
+                const int64_t f = (int64_t)k * N + n;
+                acc = fmaf(xs[k], perturbed(tw[f], s, nz[f]), acc);
+            }
         }
     }
     red[t] = acc;

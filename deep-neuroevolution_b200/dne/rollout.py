@@ -170,7 +170,10 @@ class RolloutRunner:
                             h.save_host[:h.save_m] = torch.from_numpy(loc)
                             h.save_list[:h.save_m].copy_(h.save_host[:h.save_m], non_blocking=True)
                     h.dirty = False
-                h.obs_dev.copy_(env.obs_block(h.lo, h.hi), non_blocking=True)           # pinned -> HBM
+                if hasattr(env, "device_obs"):                                           # raw frames -> device preprocess (dne/raw_env.py)
+                    h.obs_dev = env.device_obs(h.lo, h.hi)
+                else:
+                    h.obs_dev.copy_(env.obs_block(h.lo, h.hi), non_blocking=True)       # pinned -> HBM
                 if want_obstat and h.save_m:                         # es.py:358-359 on the device, unnormalised observations
                     F.check(F.lib().dne_ob_stat_accumulate(F.ptr(h.obs_dev, torch.float32), self.net.ob_dim,
                                                            F.ptr(h.save_list), h.save_m, F.ptr(h.ob_sum),

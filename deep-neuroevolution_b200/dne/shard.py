@@ -94,6 +94,17 @@ def broadcast_object(obj, src: int = 0):
     return box[0]
 
 
+def all_gather_object(obj):
+    """Every rank's picklable object, in rank order (small host-side records only: behaviour characterisations for the
+    VINE export)."""
+    _, world = dist_info()
+    if world == 1:
+        return [obj]
+    out = [None] * world
+    dist.all_gather_object(out, obj)
+    return out
+
+
 def barrier():
     _, world = dist_info()
     if world > 1:

@@ -180,6 +180,108 @@ class GenerationStats(dict):
     pass
 
 
+def vine_export_cloud(root, iteration, bc_vectors):
+    """es_modified.py:179-199 ``master_extract_cloud``: one row per offspring episode in
+    ``<root>/snapshots/snapshot_gen_{it:04}/snapshot_offspring_{it:04}.dat`` = final BC row, fitness, length, noise index,
+    policy seed, sign -- the per-generation point cloud the reference's visual_inspector reads.
+    ``bc_vectors``: iterable of (bc [t, D] or [D], fitness, length, noise_idx, policy_seed, sign) (es_modified.py:505-512)."""
+    import csv
+    import os
+    path = os.path.join(root, "snapshots", "snapshot_gen_{:04}".format(int(iteration)))
+    os.makedirs(path, exist_ok=True)
+    with open(os.path.join(path, "snapshot_offspring_{:04}.dat".format(int(iteration))), 'w+') as f:
+        writer = csv.writer(f, delimiter=' ')
+        for bc_vec, fitness, length, noise_idx, policy_seed, sign in bc_vectors:
+            last = np.asarray(bc_vec)
+            last = last[-1] if last.ndim > 1 else last
+            writer.writerow(np.hstack((last, fitness, length, noise_idx, policy_seed, sign)))
+    return path
+
+
+def vine_export_parent(root, iteration, eval_bc_vecs, eval_rets, noise_stdev, policy=None, ref_batch=None):
+    """es_modified.py:140-177 ``master_extract_parent``: the parent's snapshot (+ pickled reference batch) and the
+    evaluation episode whose return is closest to the mean as ``snapshot_parent_{it:04}.dat`` (final BC row, fitness,
+    length, seed, noise_stdev)."""
+    import csv
+    import os
+    import pickle
+    path = os.path.join(root, "snapshots", "snapshot_gen_{:04}".format(int(iteration)))
+    os.makedirs(path, exist_ok=True)
+    if policy is not None:
+        policy.save(os.path.join(path, "snapshot_parent_{:04d}.h5".format(iteration)))
+    if ref_batch is not None:
+        with open(os.path.join(path, "snapshot_parent_{:04d}_rb.p".format(iteration)), "wb") as f:
+            pickle.dump(ref_batch, f)
+    if not len(eval_rets):
+        return path
+    rets = np.asarray(eval_rets)
+    idx = int((np.abs(rets - int(np.mean(rets)))).argmin())                    # es_modified.py:165-167
+    bc_vec, fitness, length, seed = eval_bc_vecs[idx]
+    last = np.asarray(bc_vec)
+    last = last[-1] if last.ndim > 1 else last
+    with open(os.path.join(path, "snapshot_parent_{:04}.dat".format(int(iteration))), 'w+') as f:
+        csv.writer(f, delimiter=' ').writerow(np.hstack((last, fitness, length, seed, noise_stdev)))
+    return path
+
+
+class TrainingState(object):
+    """gpu_implementation/es.py:40-83,155-162,278-283: everything a run needs to continue after a restart -- iteration and
+    timestep counters, the (adaptive) timestep limit, theta, the optimizer's moments and step count, the observation
+    statistics and the noise-index stream -- pickled to ``<log_dir>/snapshot.pkl`` after every iteration and picked up by the
+    next ``run_master`` on the same ``log_dir``.  Arrays are host numpy copies (the device state is rebuilt from them)."""
+
+    FILE = 'snapshot.pkl'
+
+    def __init__(self, exp):
+        self.exp = exp
+        self.it = 0
+        self.timesteps_so_far = 0
+        self.episodes_so_far = 0
+        self.time_elapsed = 0.0
+        self.tslimit = None
+        self.theta = None
+        self.optimizer = None          # dict(kind, t, m, v)
+        self.ob_stat = None            # dict(sum, sumsq, count)
+        self.rs_state = None           # np.random.RandomState.get_state() of the noise-index stream
+
+    def capture(self, optimizer, ob_stat, rs):
+        upd = optimizer._upd
+        self.theta = upd.theta.cpu().numpy()
+        self.optimizer = dict(kind=upd.kind, t=int(upd.t), v=upd.v.cpu().numpy(),
+                              m=None if upd.m is None else upd.m.cpu().numpy())
+        self.ob_stat = None if ob_stat is None else dict(sum=ob_stat.sum.copy(), sumsq=ob_stat.sumsq.copy(), count=ob_stat.count)
+        self.rs_state = rs.get_state()
+
+    def restore(self, optimizer, ob_stat, rs):
+        upd = optimizer._upd
+        assert upd.kind == self.optimizer['kind'] and upd.P == self.theta.size
+        upd.theta.copy_(torch.from_numpy(self.theta))
+        upd.v.copy_(torch.from_numpy(self.optimizer['v']))
+        if upd.m is not None:
+            upd.m.copy_(torch.from_numpy(self.optimizer['m']))
+        upd.t = int(self.optimizer['t'])
+        upd.ctx.theta_epoch = getattr(upd.ctx, "theta_epoch", 0) + 1
+        if ob_stat is not None and self.ob_stat is not None:
+            ob_stat.sum[:], ob_stat.sumsq[:], ob_stat.count = self.ob_stat['sum'], self.ob_stat['sumsq'], self.ob_stat['count']
+        rs.set_state(self.rs_state)
+
+    def save(self, log_dir):
+        import os
+        import pickle
+        os.makedirs(log_dir, exist_ok=True)
+        tmp = os.path.join(log_dir, self.FILE + '.tmp')
+        with open(tmp, 'wb') as f:
+            pickle.dump(self, f)
+        os.replace(tmp, os.path.join(log_dir, self.FILE))
+
+    @classmethod
+    def load(cls, log_dir):
+        import os
+        import pickle
+        with open(os.path.join(log_dir, cls.FILE), 'rb') as f:
+            return pickle.load(f)
+
+
 def run_master(master_redis_cfg, log_dir, exp, *, max_iterations=None, n_slots=256, env=None, noise=None, seed=None,
                on_iteration=None):
     """es.py:141-353.  Every rank of the job calls this (rank 0 logs); returns the final flat theta (numpy) once
@@ -214,6 +316,7 @@ def run_master(master_redis_cfg, log_dir, exp, *, max_iterations=None, n_slots=2
         policy.set_ref_batch(ref_batch)
 
     tslimit, incr_tslimit_threshold, tslimit_incr_ratio, tslimit_max, adaptive_tslimit = _cutoff(config)
+    vine = bool(exp.get('vine_export'))        # es_modified.py: per-generation BC point clouds for the visual inspector
     group = 2
     runner = RolloutRunner(ctx, policy.net, env, n_slots=n_slots, group=group,
                            pipeline=2 if n_slots % 4 == 0 else 1, ref_batch=policy.ref_batch)
@@ -221,6 +324,21 @@ def run_master(master_redis_cfg, log_dir, exp, *, max_iterations=None, n_slots=2
     episodes_so_far = timesteps_so_far = 0
     tstart = time.time()
     it = 0
+    # resume (gpu_implementation/es.py:155-162): a snapshot.pkl in log_dir continues that run; written after every
+    # iteration when exp['save_training_state'] is set (rank 0 writes, every rank of a restarted job reads the same file)
+    state = TrainingState(exp)
+    keep_state = bool(exp.get('save_training_state')) and bool(log_dir)
+    if keep_state:
+        try:
+            state = TrainingState.load(log_dir)
+            state.restore(optimizer, ob_stat, rs)
+            it, timesteps_so_far, episodes_so_far = state.it, state.timesteps_so_far, state.episodes_so_far
+            if state.tslimit is not None:
+                tslimit = state.tslimit
+            if rank == 0:
+                tlogger.log('Loaded iteration {} from {}'.format(state.it, log_dir))
+        except FileNotFoundError:
+            pass
     while max_iterations is None or it < max_iterations:
         step_tstart = time.time()
         it += 1
@@ -236,6 +354,7 @@ def run_master(master_redis_cfg, log_dir, exp, *, max_iterations=None, n_slots=2
         num_eps = num_ts = 0
         ob_count_this_batch = 0
         ob_acc = None
+        vine_cloud, vine_eval = [], []
         ticks_this_iter = 0
         first = True
         # es.py:230: collect until BOTH quotas are met.  First batch = ceil(episodes_per_batch/2) pairs; if the
@@ -251,6 +370,7 @@ def run_master(master_redis_cfg, log_dir, exp, *, max_iterations=None, n_slots=2
             # the worker-side random stream (es.py:372: action noise, ob-stat sampling) is separate from the seeded
             # noise-index stream, so the index sequence never depends on episode lengths or the rank count
             res = runner.run(optimizer.device_theta, units[lo:hi], tslimit, ob_mean=ob_mean, ob_std=ob_std,
+                             collect_bc="final" if vine else None,
                              ac_noise_std=getattr(policy, "ac_noise_std", 0.0),
                              random_stream=np.random.RandomState((seed + 1000 * it + rank) % (2 ** 31)),
                              save_obs_prob=config.calc_obstat_prob if policy.needs_ob_stat else 0.0)
@@ -258,6 +378,13 @@ def run_master(master_redis_cfg, log_dir, exp, *, max_iterations=None, n_slots=2
                 acc = np.concatenate([res.ob_sum, res.ob_sumsq, [float(res.ob_count)]])
                 ob_acc = acc if ob_acc is None else ob_acc + acc
             ticks_this_iter += res.ticks
+            if vine:                       # es_modified.py:505-512: (bc, return, length, noise_idx, policy_seed, sign) per episode
+                mine = [(res.bcs[u][g], float(res.returns[u, g]), int(res.lengths[u, g]),
+                         int(units[lo + u].noise_idx), 0, 1 if g == 0 else -1, lo + u >= n_pairs)
+                        for u in range(hi - lo) for g in range(2)]
+                for part in (shard.all_gather_object(mine) if world > 1 else [mine]):
+                    vine_cloud += [p[:6] for p in part if not p[6]]
+                    vine_eval += [(p[0], p[1], p[2], 0) for p in part if p[6]][:max(0, n_eval - len(vine_eval))]
             dev = upd.device
             pack = torch.from_numpy(np.concatenate([res.returns, res.signreturns, res.lengths.astype(np.float32)],
                                                    axis=1)).to(dev)
@@ -332,6 +459,16 @@ def run_master(master_redis_cfg, log_dir, exp, *, max_iterations=None, n_slots=2
                                          signreturns_n2=signreturns_n2, g=g, theta=optimizer.device_theta,
                                          forward_launches=ticks_this_iter, ob_stat=ob_stat,
                                          slots_per_launch=n_slots // len(runner.halves)))
+        if vine and rank == 0 and log_dir:                                                # es_modified.py:140-199
+            vine_export_cloud(log_dir, it, vine_cloud)
+            vine_export_parent(log_dir, it, vine_eval, [e[1] for e in vine_eval], config.noise_stdev)
+        if keep_state:                                                                    # gpu_implementation/es.py:278-283
+            state.it, state.timesteps_so_far, state.episodes_so_far = it, timesteps_so_far, episodes_so_far
+            state.tslimit, state.time_elapsed = tslimit, step_tend - tstart
+            state.capture(optimizer, ob_stat, rs)
+            if rank == 0:
+                state.save(log_dir)
+            shard.barrier()
         if rank == 0 and log_dir and config.snapshot_freq != 0 and it % config.snapshot_freq == 0:   # es.py:345-353
             import os.path as osp
             filename = osp.join(log_dir, 'snapshot_iter{:05d}_rew{}.h5'.format(

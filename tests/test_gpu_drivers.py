@@ -292,3 +292,92 @@ def test_deep_ga_validation_and_elite_selection(noise, host_noise, tmp_path):
         assert new_elite in parents and len(parents) == 4
         assert all(1 <= len(g) <= it for g in genomes)                            # offspring = one mutation of a cached parent
         elite = new_elite
+
+
+def test_es_training_state_resume_is_bit_identical(noise, tmp_path):
+    """gpu_implementation/es.py:155-162,278-283: snapshot.pkl (theta, optimizer moments + step count, counters, the
+    noise-index stream) after every iteration; a restarted run_master on the same log_dir continues exactly where the first
+    one stopped: 1 iteration + restart + 1 iteration == 2 iterations, bit for bit (deterministic environment)."""
+    from es_distributed import es as ES
+    from dne.envs import DeterministicAtariEnv
+    exp = json.loads(json.dumps(FROSTBITE_ES))
+    exp["policy"]["type"] = "GAAtariPolicy"
+    exp["config"]["eval_prob"] = 0.0
+    exp["save_training_state"] = True
+    ES.set_default_noise(noise)
+
+    def run(log_dir, iters):
+        return ES.run_master(None, str(log_dir), json.loads(json.dumps(exp)), max_iterations=iters, n_slots=8,
+                             env=DeterministicAtariEnv(8, episode_len=6, seed=3), noise=noise, seed=11)
+    straight = run(tmp_path / "a", 2)
+    run(tmp_path / "b", 1)
+    st = ES.TrainingState.load(str(tmp_path / "b"))
+    assert st.it == 1 and st.optimizer["t"] == 1 and st.theta.shape == straight.shape
+    resumed = run(tmp_path / "b", 2)
+    np.testing.assert_array_equal(resumed, straight)
+    assert ES.TrainingState.load(str(tmp_path / "b")).it == 2
+
+
+def test_raw_frame_env_device_pipeline_matches_reference_wrappers():
+    """dne/raw_env.py: emulators on a host thread pool + max / gray / Pillow-exact 84x84 warp / frame stack on the device
+    against the reference's wrapper chain restated on the CPU (atari_wrappers.py:86-107 MaxAndSkipEnv, :129-142 WarpFrame,
+    :167-180 FrameStack) fed with the SAME emulator frames: bit-exact uint8 stacks after resets and steps."""
+    from dne.raw_env import SyntheticEmulator, RawFrameAtariEnv
+    n = 6
+    env = RawFrameAtariEnv([SyntheticEmulator(100 + s, frames=40) for s in range(n)], noop_max=3, seed=1, device="cuda:0")
+    twin = [SyntheticEmulator(100 + s, frames=40) for s in range(n)]            # CPU replica of every emulator
+    rs_noop = np.random.RandomState(1)
+    stacks = np.zeros((n, 84, 84, 4), dtype=np.uint8)
+
+    def cpu_reset(slots):
+        noops = rs_noop.randint(1, 4, size=len(slots))
+        for s, k in zip(slots, noops):
+            f = twin[s].reset()
+            for _ in range(k):
+                _, over, f = twin[s].act(0)
+                if over:
+                    f = twin[s].reset()
+            twin[s].last = f
+            stacks[s] = O.warp_frame_cpu(f)[:, :, None]                           # FrameStack._reset: first frame x 4
+
+    def cpu_step(slots, actions):
+        for s, a in zip(slots, actions):
+            prev = cur = twin[s].last
+            for _ in range(4):
+                _, over, f = twin[s].act(int(a))
+                prev, cur = cur, f
+                if over:
+                    break
+            twin[s].last = cur
+            w = O.warp_frame_cpu(np.maximum(prev, cur))                           # MaxAndSkipEnv + WarpFrame
+            stacks[s, :, :, :3] = stacks[s, :, :, 1:]
+            stacks[s, :, :, 3] = w
+    all_slots = np.arange(n)
+    env.reset(all_slots)
+    cpu_reset(all_slots)
+    np.testing.assert_array_equal(env.device_obs(0, n).cpu().numpy(), stacks)
+    rs = np.random.RandomState(2)
+    for t in range(5):
+        acts = rs.randint(0, 18, size=n)
+        env.step(all_slots, acts)
+        cpu_step(all_slots, acts)
+        if t == 2:                                                                # mid-run reset of two slots
+            env.reset(np.array([1, 4]))
+            cpu_reset([1, 4])
+        np.testing.assert_array_equal(env.device_obs(0, n).cpu().numpy(), stacks)
+
+
+def test_es_run_master_on_raw_frame_env(noise, tmp_path):
+    """The ES driver end to end on raw frames: thread-pool emulators, device preprocess, tensor-core forward, update."""
+    from es_distributed import es as ES
+    from dne.raw_env import make_synthetic_raw_env
+    exp = json.loads(json.dumps(FROSTBITE_ES))
+    exp["policy"]["type"] = "GAAtariPolicy"
+    exp["config"].update(eval_prob=0.0, episodes_per_batch=8, episode_cutoff_mode=6)
+    ES.set_default_noise(noise)
+    env = make_synthetic_raw_env(8, seed=2, frames=400, noop_max=2, device="cuda:0")
+    log = []
+    theta = ES.run_master(None, str(tmp_path), exp, max_iterations=2, n_slots=8, env=env, noise=noise, seed=4,
+                          on_iteration=lambda it, stats, extra: log.append(dict(stats)))
+    assert len(log) == 2 and np.isfinite(theta).all()
+    assert log[0]["EpLenMean"] == 6 and log[1]["TimestepsSoFar"] == 2 * 8 * 6

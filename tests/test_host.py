@@ -194,6 +194,27 @@ def test_cpu_worker_sample_runs():
     assert g.shape == (net.num_params,) and g.dtype == np.float32
 
 
+def test_tensorboard_event_file(tmp_path):
+    """tabular_logger.py:17-52,150-152: every dumped row also lands in a TensorBoard event file (TFRecord framing with
+    masked CRC-32C, Event / Summary protobufs written without TensorFlow).  CRC-32C known answer: "123456789" -> 0xE3069283."""
+    import glob
+    from es_distributed import tabular_logger as tl
+    assert tl._crc32c(b"123456789") == 0xE3069283
+    tl.set_quiet(True)
+    tl.start(str(tmp_path))
+    for i in range(3):
+        tl.record_tabular("EpRewMean", 10.5 * i)
+        tl.record_tabular("TimestepsSoFar", 1000 * (i + 1))
+        tl.record_tabular("Note", "text values are skipped")
+        tl.dump_tabular()
+    tl.stop()
+    files = glob.glob(os.path.join(str(tmp_path), "events.out.tfevents.*"))
+    assert len(files) == 1
+    ev = tl.read_tb_events(files[0])
+    assert [s for s, _ in ev] == [1, 2, 3]
+    assert ev[2][1] == {"EpRewMean": 21.0, "TimestepsSoFar": 3000.0}
+
+
 def test_tabular_logger(tmp_path):
     from es_distributed import tabular_logger as tl
     tl.start(str(tmp_path))
@@ -286,3 +307,20 @@ def test_get_ref_batch_host_env():
     assert len(rb) == 5 and all(f.shape == (84, 84, 4) and f.dtype == np.uint8 for f in rb)
     rb[0][:] = 7
     assert not np.all(env.pool.numpy()[:, 0] == 7)
+
+
+def test_vine_export_files(tmp_path):
+    """es_modified.py:140-199: per-generation offspring cloud and parent row in the visual inspector's layout."""
+    from es_distributed.es import vine_export_cloud, vine_export_parent
+    rs = np.random.RandomState(0)
+    cloud = [(rs.randint(0, 256, size=(5, 128)).astype(np.uint8), 30.0, 5, 1234, 0, 1),
+             (rs.randint(0, 256, size=128).astype(np.uint8), 10.0, 7, 1234, 0, -1)]
+    path = vine_export_cloud(str(tmp_path), 3, cloud)
+    rows = [l.split() for l in open(os.path.join(path, "snapshot_offspring_0003.dat"))]
+    assert len(rows) == 2 and len(rows[0]) == 128 + 5
+    assert [float(x) for x in rows[0][128:]] == [30.0, 5.0, 1234.0, 0.0, 1.0]
+    assert [int(float(x)) for x in rows[0][:128]] == cloud[0][0][-1].tolist()      # bc_vec[-1]: the final BC row
+    evals = [(cloud[0][0], 30.0, 5, 0), (cloud[1][0], 10.0, 7, 0), (cloud[1][0], 22.0, 6, 0)]
+    vine_export_parent(str(tmp_path), 3, evals, [30.0, 10.0, 22.0], 0.02)
+    row = open(os.path.join(path, "snapshot_parent_0003.dat")).read().split()
+    assert float(row[128]) == 22.0 and float(row[-1]) == 0.02                      # closest to int(mean) = 20 is 22
