@@ -57,7 +57,10 @@ def cli():
 @click.option('--max_iterations', type=int, default=None)
 @click.option('--n_slots', type=int, default=256)
 @click.option('--seed', type=int, default=None)
-def master(algo, exp_str, exp_file, master_socket_path, log_dir, max_iterations, n_slots, seed):
+@click.option('--allow_synthetic_env', is_flag=True, default=False,
+              help='no gym/ALE/MuJoCo backend is registered in this build: run real env ids on the synthetic stand-in '
+                   '(throughput only; sets exp["allow_synthetic_env"])')
+def master(algo, exp_str, exp_file, master_socket_path, log_dir, max_iterations, n_slots, seed, allow_synthetic_env):
     # main.py:48-61
     assert (exp_str is None) != (exp_file is None), 'Must provide exp_str xor exp_file to the master'
     if exp_str:
@@ -65,6 +68,8 @@ def master(algo, exp_str, exp_file, master_socket_path, log_dir, max_iterations,
     else:
         with open(exp_file, 'r') as f:
             exp = json.loads(f.read())
+    if allow_synthetic_env:
+        exp['allow_synthetic_env'] = True
     rank, world, local = shard.init_from_env()
     log_dir = os.path.expanduser(log_dir) if log_dir else '/tmp/es_master_{}'.format(os.getpid())
     if rank == 0:

@@ -324,3 +324,17 @@ def test_vine_export_files(tmp_path):
     vine_export_parent(str(tmp_path), 3, evals, [30.0, 10.0, 22.0], 0.02)
     row = open(os.path.join(path, "snapshot_parent_0003.dat")).read().split()
     assert float(row[128]) == 22.0 and float(row[-1]) == 0.02                      # closest to int(mean) = 20 is 22
+
+
+def test_make_env_real_ids_need_opt_in(monkeypatch):
+    """a real env id must not silently run on the synthetic stand-in."""
+    from dne import envs
+    monkeypatch.delenv("DNE_ALLOW_SYNTHETIC_ENV", raising=False)
+    for env_id in ("FrostbiteNoFrameskip-v4", "Humanoid-v1"):
+        with pytest.raises(KeyError, match="allow_synthetic_env"):
+            envs.make_env(env_id, 4)
+        e = envs.make_env(env_id, 4, allow_synthetic=True, episode_len=3)
+        assert getattr(e, "synthetic", False) and e.n_slots == 4
+    assert envs.make_env("SyntheticAtariFrostbite", 2, episode_len=3).n_slots == 2       # explicit synthetic ids need no flag
+    with pytest.raises(KeyError):
+        envs.make_env("NoSuchEnv-v0", 2)
