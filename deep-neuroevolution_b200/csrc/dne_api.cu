@@ -283,6 +283,15 @@ extern "C" int dne_theta_prepare(dne_ctx* ctx, const dne_net_desc* net, const fl
     return DNE_OK;
 }
 
+// Drops the prepared-theta entries of a workspace (call when a workspace is allocated or freed: entries are keyed by
+// ADDRESS, and an allocator may hand a freed workspace's address to a new one).
+extern "C" int dne_theta_forget(dne_ctx* ctx, const void* d_ws) {
+    DNE_CHECK_ARG(ctx, "ctx is null");
+    for (int i = 0; i < DNE_MAX_PREP; ++i)
+        if (ctx->prep[i].ws == d_ws || d_ws == nullptr) ctx->prep[i].ws = nullptr, ctx->prep[i].theta = nullptr;
+    return DNE_OK;
+}
+
 static int forward_impl(dne_ctx* ctx, const dne_net_desc* net, const float* d_theta, const int64_t* d_noise_idx,
                         const float* d_scale, const int32_t* d_theta_idx, const uint8_t* d_active, int n_slots,
                         int paired, const void* d_obs, const float* d_ob_mean, const float* d_ob_std,

@@ -655,10 +655,14 @@ int dne_launch_conv_layer_simt(const SlotArgs& sa, const dne_layer_desc& L, cons
 
 // ---- dense-layer planning (shared by the ws query and the launcher) -----------------------------------
 int g_dne_gemv_chunk_kb = 1024;    // dne_set_option("gemv_chunk_kb", v): bytes of weights per GEMV work item (and per partial)
-static int pick_rows_per_chunk(int K, int N) {
+static int pick_rows_per_chunk(int K, int N, int groups, int sm_count) {
     // target ~1 MB of noise per work item (persistent bulk-copy GEMV; r02 A/B: same GEMV time as 512 KB, half the partials
     // for the combine kernel to read), prefer exact divisors of K
-    int target = (int)(((size_t)g_dne_gemv_chunk_kb * 1024) / ((size_t)N * 4));
+    // ... but keep >= ~6 work items per persistent CTA (2 per SM): with fewer, the last partial round of the static
+    // schedule costs more than the halved partial traffic saves (62 pairs x 16 items = 3.35 per CTA -> 84 % busy)
+    size_t chunk_bytes = (size_t)g_dne_gemv_chunk_kb * 1024;
+    while (chunk_bytes > 256 * 1024 && (size_t)groups * ((size_t)K * N * 4 / chunk_bytes) < (size_t)12 * sm_count) chunk_bytes /= 2;
+    int target = (int)(chunk_bytes / ((size_t)N * 4));
     if (target > 512) target = 512;           // GB_MAX_ROWS of gemv_bulk.cu (x staging buffer)
     if (target < 8) target = 8;
     if (target >= K) return K;
@@ -677,17 +681,19 @@ DensePlan dne_plan_dense(const dne_layer_desc& L, int n_slots, int paired, bool 
     // paired bit 0: slots (2p,2p+1) share the noise index; bit 1: they share the theta row (GA parent)
     p.G = (paired & 1) ? 2 : 1;
     p.Gt = shared_theta ? 0 : ((paired & 2) ? 2 : 1);
-    // split-K so that the GEMM grid reaches ~2 waves
-    const int tiles = ((n_slots + DG_BM - 1) / DG_BM) * ((N + DG_BN - 1) / DG_BN);
+    // split-K so that the GEMM grid is one wave of the TMA-fed kernel (one CTA per SM, each owning a PAIR of 128-row M tiles
+    // of one N tile: theta_gemm_tma.cu) = two waves of the 128x128-tile kernels at M = 256
+    const int m_tiles = (n_slots + DG_BM - 1) / DG_BM;
+    const int tiles = ((m_tiles + 1) / 2) * ((N + DG_BN - 1) / DG_BN);
     const int k_tiles = (K + DG_BK - 1) / DG_BK;
-    int split = (2 * sm_count + tiles - 1) / tiles;
+    int split = (sm_count + tiles - 1) / tiles;
     if (split > k_tiles) split = k_tiles;
     if (split < 1) split = 1;
     int kt_per = (k_tiles + split - 1) / split;
     kt_per += kt_per & 1;                                // k_per_split % 32 == 0: the TMA-fed fp16 GEMM moves K chunks of 32
     p.k_per_split = kt_per * DG_BK;
     p.n_split = (K + p.k_per_split - 1) / p.k_per_split;
-    p.rows_per_chunk = pick_rows_per_chunk(K, N);
+    p.rows_per_chunk = pick_rows_per_chunk(K, N, (n_slots + p.G - 1) / p.G, sm_count);
     p.n_chunks = (K + p.rows_per_chunk - 1) / p.rows_per_chunk;
     const int nq = N / 4;
     p.rw = 1;

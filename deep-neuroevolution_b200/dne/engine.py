@@ -41,6 +41,7 @@ class SlotForward:
         nb = C.c_size_t()
         F.check(F.lib().dne_forward_ws_bytes(C.byref(net.desc), n_slots, C.byref(nb)))
         self.ws = _dev_bytes(nb.value, dev)
+        F.check(F.lib().dne_theta_forget(ctx.handle, F.ptr(self.ws)))     # a recycled address must not inherit a prepared entry
         self.vbn = None
         self.vbn_ws = None
         if net.vbn_len:

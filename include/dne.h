@@ -140,6 +140,9 @@ int dne_perturb_forward_conv(dne_ctx* ctx, const dne_net_desc* net, const float*
  * write to d_theta call it again.  Without a current entry the forward is still correct (thread-staged GEMM). */
 int dne_theta_prepare(dne_ctx* ctx, const dne_net_desc* net, const float* d_theta, int n_slots, void* d_ws, size_t ws_bytes,
                       void* stream);
+/* Entries are keyed by the workspace ADDRESS: forget them when a workspace is allocated or freed (an allocator may hand a
+ * freed workspace's address to a new one).  d_ws == NULL forgets every entry of the context. */
+int dne_theta_forget(dne_ctx* ctx, const void* d_ws);
 
 /* Phase-shifted double buffering of two slot tables on two CUDA streams: the NEXT dne_perturb_forward_* call on ctx
  * makes its stream wait for wait_event (cudaEvent_t, nullable) before its first kernel and records record_event
