@@ -63,7 +63,7 @@ constexpr int S2D_THREADS = S2D_STAGE_THREADS + S2D_EPI_THREADS + 96;   // + MMA
 constexpr int S2D_FRAME_BYTES = 84 * 84 * 4;                            // the uint8 frame stack of the first layer
 constexpr int S2D_FRAME_STRIDE = (S2D_FRAME_BYTES + 127) / 128 * 128;
 constexpr int S2D_MAX_GROUPS = 8;
-constexpr int S2D_MAX_BST = 4;
+constexpr int S2D_MAX_BST = 8;       // ring depth: a stage cycles through TMA latency -> conversion -> MMA, ~4.6K cycles (conv3): 4 stages were the limit
 constexpr int S2D_SMEM_BUDGET = 226 * 1024;
 
 constexpr int cmin(int a, int b) { return a < b ? a : b; }

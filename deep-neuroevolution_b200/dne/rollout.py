@@ -90,6 +90,7 @@ class RolloutRunner:
         self.halves = [_Half(ctx, net, i * per, (i + 1) * per, n_ref) for i in range(pipeline)]
         self.ref_batch = ref_batch
         self.use_theta_idx = False
+        self.action_fn = None          # optional host map from the network's output rows to environment actions
 
     # ---------------------------------------------------------------------------------------------------
     def run(self, theta: torch.Tensor, units: List[Unit], timestep_limit: Optional[int] = None, *, ob_mean=None,
@@ -190,6 +191,8 @@ class RolloutRunner:
             h.launched = False
             loc = np.nonzero(h.active)[0]
             acts = h.act_host.numpy()[loc]
+            if self.action_fn is not None:                             # discretised MuJoCo heads: scores -> bin values
+                acts = self.action_fn(acts)
             if ac_noise_std != 0.0 and random_stream is not None and acts.dtype != np.int32:
                 noisy = ~h.noiseless[loc]                             # evaluation episodes act without noise (es.py:388-391)
                 acts = acts + (random_stream.randn(*acts.shape).astype(np.float32) * np.float32(ac_noise_std)) * \

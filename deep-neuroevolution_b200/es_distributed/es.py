@@ -320,6 +320,8 @@ def run_master(master_redis_cfg, log_dir, exp, *, max_iterations=None, n_slots=2
     group = 2
     runner = RolloutRunner(ctx, policy.net, env, n_slots=n_slots, group=group,
                            pipeline=2 if n_slots % 4 == 0 else 1, ref_batch=policy.ref_batch)
+    if getattr(policy, "_bin_values", None) is not None:
+        runner.action_fn = policy.action_fn
 
     episodes_so_far = timesteps_so_far = 0
     tstart = time.time()

@@ -317,7 +317,7 @@ class LargeModelPolicy(GAAtariPolicy):
 
 
 class MujocoPolicy(Policy):
-    """policies.py:122-302 ('ff' connection, 'continuous:' head)."""
+    """policies.py:122-302 ('ff' connection; 'continuous:', 'uniform:N' and 'custom:v0,..,vk' action heads)."""
 
     def _initialize(self, ob_space, ac_space, ac_bins, ac_noise_std, nonlin_type, hidden_dims, connection_type):
         self.ac_space = ac_space
@@ -327,11 +327,32 @@ class MujocoPolicy(Policy):
         self.connection_type = connection_type
         assert len(ob_space.shape) == len(ac_space.shape) == 1
         assert connection_type == 'ff'
-        mode, _ = ac_bins.split(':')
-        if mode != 'continuous':
-            raise NotImplementedError("only the 'continuous:' action head is built (configurations/humanoid*.json)")
-        return N.make_net("MujocoPolicy", ob_dim=ob_space.shape[0], hidden=tuple(hidden_dims), ac_dim=ac_space.shape[0],
+        mode, arg = ac_bins.split(':')
+        adim = ac_space.shape[0]
+        low, high = np.asarray(ac_space.low, np.float32), np.asarray(ac_space.high, np.float32)
+        self._bin_values = None                       # [adim, num_bins] action value of every bin (discretised heads)
+        if mode == 'uniform':                         # policies.py:166-171: bins evenly spaced from low to high
+            nb = int(arg)
+            self._bin_values = (np.float32(1.0 / (nb - 1.0)) * np.arange(nb, dtype=np.float32)[None, :] * (high - low)[:, None]
+                                + low[:, None]).astype(np.float32)
+        elif mode == 'custom':                        # policies.py:173-190: listed values in [-1, 1] rescaled to [low, high]
+            k = np.array(list(map(float, arg.split(','))), dtype=np.float32)
+            assert k.ndim == 1 and k[0] == -1 and k[-1] == 1
+            self._bin_values = ((high - low)[:, None] / (k[-1] - k[0]) * (k - k[0])[None, :] + low[:, None]).astype(np.float32)
+        elif mode != 'continuous':
+            raise NotImplementedError(mode)
+        out_dim = adim if self._bin_values is None else adim * self._bin_values.shape[1]   # bins(): dense to dim*num_bins (:116-119)
+        return N.make_net("MujocoPolicy", ob_dim=ob_space.shape[0], hidden=tuple(hidden_dims), ac_dim=out_dim,
                           nonlin=nonlin_type)
+
+    def action_fn(self, scores: np.ndarray) -> np.ndarray:
+        """Network output -> action.  'continuous:': identity.  Discretised heads (policies.py:116-119,166-190): per action
+        dimension the argmax over its bins' scores (first maximum), mapped to that bin's value."""
+        if self._bin_values is None:
+            return scores
+        adim, nb = self._bin_values.shape
+        idx = np.argmax(np.asarray(scores).reshape(-1, adim, nb), axis=2)
+        return self._bin_values[np.arange(adim)[None, :], idx]
 
     def _layer_names(self):
         return ["l{}".format(i) for i in range(len(self.hidden_dims))] + ["out"]
@@ -343,7 +364,7 @@ class MujocoPolicy(Policy):
         return theta
 
     def act(self, ob, random_stream=None):
-        a = self._forward_noiseless(np.asarray(ob, dtype=np.float32))
+        a = self.action_fn(self._forward_noiseless(np.asarray(ob, dtype=np.float32)))
         if random_stream is not None and self.ac_noise_std != 0:
             a += random_stream.randn(*a.shape) * self.ac_noise_std          # policies.py:204-205
         return a

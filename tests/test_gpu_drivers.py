@@ -381,3 +381,24 @@ def test_es_run_master_on_raw_frame_env(noise, tmp_path):
                           on_iteration=lambda it, stats, extra: log.append(dict(stats)))
     assert len(log) == 2 and np.isfinite(theta).all()
     assert log[0]["EpLenMean"] == 6 and log[1]["TimestepsSoFar"] == 2 * 8 * 6
+
+
+def test_mujoco_discretised_action_heads():
+    """policies.py:116-119,166-190: 'uniform:N' and 'custom:...' heads -- a dense layer to adim*num_bins scores, per action
+    dimension the argmax bin, mapped to evenly spaced / listed values rescaled to [low, high]."""
+    from dne.envs import Box
+    from es_distributed import policies
+    ob, ac = Box(-np.inf, np.inf, (5,)), Box(np.array([-0.4, -1.0, 0.0], np.float32), np.array([0.4, 1.0, 2.0], np.float32))
+    kw = dict(ac_noise_std=0.0, nonlin_type="tanh", hidden_dims=[8], connection_type="ff")
+    pu = policies.MujocoPolicy(ob, ac, ac_bins="uniform:5", **kw)
+    assert pu.net.n_out == 3 * 5
+    scores = np.zeros((2, 3, 5), np.float32)
+    scores[0, 0, 4] = scores[0, 1, 0] = scores[0, 2, 2] = 1.0
+    scores[1, :, 1] = 1.0
+    a = pu.action_fn(scores.reshape(2, 15))
+    np.testing.assert_allclose(a[0], [0.4, -1.0, 1.0], rtol=1e-6)
+    np.testing.assert_allclose(a[1], [-0.4 + 0.25 * 0.8, -1.0 + 0.25 * 2.0, 0.5], rtol=1e-6)
+    pc = policies.MujocoPolicy(ob, ac, ac_bins="custom:-1,-0.5,0,1", **kw)
+    assert pc.net.n_out == 3 * 4
+    a = pc.action_fn(np.eye(4, dtype=np.float32)[[1, 3, 0]].reshape(1, 12))
+    np.testing.assert_allclose(a[0], [-0.2, 1.0, 0.0], rtol=1e-6)

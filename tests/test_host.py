@@ -338,3 +338,4 @@ def test_make_env_real_ids_need_opt_in(monkeypatch):
     assert envs.make_env("SyntheticAtariFrostbite", 2, episode_len=3).n_slots == 2       # explicit synthetic ids need no flag
     with pytest.raises(KeyError):
         envs.make_env("NoSuchEnv-v0", 2)
+
