@@ -185,11 +185,23 @@ def run_b200(args):
 
     KERNELS_PER_TICK = 6          # conv1-3, theta GEMM, noise GEMV, combine+head (LargeModel, default options)
     USE_GRAPH = os.environ.get("DNE_BENCH_GRAPH", "1") == "1"       # r02 A/B at T=200: 639K vs 612K env-steps/s
+    if NS >= 2 and PHASED:
+        USE_GRAPH = False        # the phase-event hand-off between slot tables (cross-stream events) is not captured
     PROF_EVERY = 16 if USE_GRAPH else 1
     graphs = {}
     prof_state = {"on": False}
 
+    BREAKDOWN = os.environ.get("DNE_BENCH_BREAKDOWN", "0") == "1"     # diagnostic: adds synchronisations, not a bench value
+    bd = []
+
+    def mark(tag, sync=True):
+        if BREAKDOWN:
+            if sync:
+                torch.cuda.synchronize()
+            bd.append((tag, time.perf_counter()))
+
     def generation_value():
+        mark("start")
         idx_all = np.array([noise.sample_index(idx_stream, P) for _ in range(n_pairs)], dtype=np.int64)
         my = idx_all[lo:hi]
         returns = torch.zeros(len(my), 2, device=dev)
@@ -229,6 +241,7 @@ def run_b200(args):
                          obs_ptr[r][h], None, a[3], a[4], a[5], a[6], stream_ptr[h])
                 if rc:
                     F.check(rc)
+            mark("wave_setup")
             for t in range(T):
                 r = t % R
                 for h in live:
@@ -258,8 +271,10 @@ def run_b200(args):
                         else:
                             tick(h, r)
                 ret_acc.add_(rew_pool[t % 64])                     # one bookkeeping op per tick, main stream
+            mark("ticks_enqueued", sync=False)
             for s in streams:
                 cur.wait_stream(s)
+            mark("ticks_done")
             r = torch.cat([ret_acc[h * part:h * part + 2 * len(parts[h])] for h in range(NS)]).view(-1, 2)
             returns[w0:w0 + npw] = r
         allret = shard.all_gather_rows(returns, n_pairs)
@@ -267,6 +282,11 @@ def run_b200(args):
         g = upd.gradient(proc[lo:hi].contiguous(), torch.from_numpy(my).to(dev), denom=2 * n_pairs)
         shard.all_reduce_sum_(g)
         upd.step(L2)
+        mark("update")
+        if BREAKDOWN and rank == 0:
+            t0 = bd[0][1]
+            print("[breakdown] " + "  ".join(f"{tag}=+{(t - t0) * 1e3:.2f}ms" for tag, t in bd[1:]), file=sys.stderr, flush=True)
+        bd.clear()
 
     def timed(fn, steps, warmup, profile=False):
         for _ in range(warmup):
@@ -395,6 +415,8 @@ def run_b200(args):
             "config": {"workload": f"frostbite_es_pop{args.pop}_LargeModel_T{T}",
                        "population": args.pop, "noise_pairs": n_pairs, "policy": "LargeModel (P=4052658, 18 actions)",
                        "env_slots_per_gpu": slots, "slot_tables": NS, "episode_len": T, "noise_table": args.noise_count,
+                       "tick_launch": "CUDA graph replay (6 kernels; every 16th tick kernel by kernel for the CUDA-event GEMV timing)"
+                                      if USE_GRAPH else "kernel by kernel",
                        "sharding": f"population over {world} rank(s); all_gather(returns)+all_reduce(g)",
                        "l2": "inputs larger than L2 (>=1 GB of noise slices streamed per tick)",
                        "step": "one generation (rollouts + update)"},

@@ -81,6 +81,7 @@ extern "C" int dne_set_option(const char* name, int value) {
     if (strcmp(name, "theta_tma") == 0) { g_dne_theta_tma = value ? 1 : 0; return DNE_OK; }
     if (strcmp(name, "gemv_stages") == 0 && value >= 2 && value <= 8) { extern int g_dne_gemv_stages; g_dne_gemv_stages = value; return DNE_OK; }
     if (strcmp(name, "gemv_prefetch") == 0 && value >= 0 && value <= 256) { extern int g_dne_gemv_prefetch; g_dne_gemv_prefetch = value; return DNE_OK; }
+    if (strcmp(name, "gemv_grid") == 0 && value >= 0) { extern int g_dne_gemv_grid; g_dne_gemv_grid = value; return DNE_OK; }
     if (strcmp(name, "gemv_ctas_per_sm") == 0 && value >= 1 && value <= 2) { g_dne_gemv_ctas_per_sm = value; return DNE_OK; }
     dne_set_error("dne_set_option: unknown option '%s'", name);
     return DNE_ERR_ARG;

@@ -21,6 +21,7 @@ using namespace tc05;
 
 int g_dne_gemv_bulk = 1;
 int g_dne_gemv_ctas_per_sm = 2;
+int g_dne_gemv_grid = 0;             // > 0: cap on the number of CTAs (dne_set_option("gemv_grid")): leaves whole SMs to another stream
 int g_dne_gemv_stages = 6;           // shared-memory ring depth (2..GB_STAGES), dne_set_option("gemv_stages")
 int g_dne_gemv_prefetch = 0;         // L2 prefetch distance in stages (cp.async.bulk.prefetch.L2), dne_set_option("gemv_prefetch")
 
@@ -253,6 +254,7 @@ int dne_launch_gemv_bulk(const SlotArgs& sa, const GemvSrc& src, int G, const fl
     const size_t smem = (size_t)n_stages * GB_STAGE_BYTES + (size_t)RW * G * (N + 4) * sizeof(float) + 128;
     const int n_items = n_groups * n_chunks;
     int grid = g_dne_gemv_ctas_per_sm * sm_count;   // 1 CTA/SM leaves room for the other stream's conv CTAs to co-reside
+    if (g_dne_gemv_grid > 0 && grid > g_dne_gemv_grid) grid = g_dne_gemv_grid;
     if (grid > n_items) grid = n_items;
     int dev = 0;
     cudaGetDevice(&dev);
