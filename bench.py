@@ -283,9 +283,9 @@ def run_b200(args):
         shard.all_reduce_sum_(g)
         upd.step(L2)
         mark("update")
-        if BREAKDOWN and rank == 0:
+        if BREAKDOWN:
             t0 = bd[0][1]
-            print("[breakdown] " + "  ".join(f"{tag}=+{(t - t0) * 1e3:.2f}ms" for tag, t in bd[1:]), file=sys.stderr, flush=True)
+            print(f"[breakdown r{rank}] " + "  ".join(f"{tag}=+{(t - t0) * 1e3:.2f}ms" for tag, t in bd[1:]), file=sys.stderr, flush=True)
         bd.clear()
 
     def timed(fn, steps, warmup, profile=False):

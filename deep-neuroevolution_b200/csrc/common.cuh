@@ -64,6 +64,35 @@ void dne_set_error(const char* fmt, ...);
         }                                                                              \
     } while (0)
 
+// ---- programmatic dependent launch (PDL) of the tick's kernel chain -----------------------------------------------
+// conv1 -> conv2 -> conv3 -> theta GEMM -> noise GEMV -> combine+head run back to back on one stream.  Kernels 2..6 are
+// launched with cudaLaunchAttributeProgrammaticStreamSerialization: every kernel of the chain calls pdl_trigger() first
+// thing (the NEXT launch may be scheduled as soon as all CTAs of this grid have started), sets itself up (barriers, TMEM,
+// weight prefetch: nothing that an upstream kernel of the tick writes) and calls pdl_wait() before the first access to
+// upstream data or to any global buffer it writes.  pdl_wait() returns when the previous grid has completed and flushed --
+// which itself waited for ITS predecessor, so completion is transitive along the chain.  The launch latency and the
+// prologue of kernel i+1 overlap the tail of kernel i.  dne_set_option("pdl", 0) launches the chain fully serialized.
+extern int g_dne_pdl;
+template <typename... KArgs, typename... Args>
+static inline cudaError_t dne_launch_chain(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool dependent,
+                                           Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = (dependent && g_dne_pdl) ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, args...);
+}
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#endif
+
 static inline int64_t cdiv64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 

@@ -144,7 +144,11 @@ struct S2dOut {
 template <int CIN, int COUT, int KS, int S, int HIN, int HOUT, int PAD, bool IN_U8>
 __global__ void __launch_bounds__(S2D_THREADS, 1)
 conv_s2d_kernel(SlotArgs sa, int64_t off_w, LayerEpi epi, const void* __restrict__ in_base, int64_t in_slot_stride,
-                S2dOut so, int n_slots) {
+                S2dOut so, int n_slots, int vdiv, int in_mod) {
+    // vdiv > 1 (virtual-batch-norm reference pass, vbn_kernels.cu): the launch covers n_slots = members * vdiv VIRTUAL
+    // slots; virtual slot v is image v % vdiv of member v / vdiv -- the member indexes the slot table (theta row, noise
+    // index, scale, active flag, BN statistics), v indexes the input / output buffers.  in_mod > 0: the first layer's frames
+    // are shared by all members (frame v % in_mod).
     using Cfg = S2dCfg<CIN, COUT, KS, S, HIN, HOUT, PAD, IN_U8>;
     constexpr int NG = Cfg::NG, NSTB = Cfg::NSTB, MT = Cfg::MT, NTAP = Cfg::NTAP, W = Cfg::W, KT = Cfg::KT;
     constexpr int TPC = Cfg::TPC, NCPG = Cfg::NCPG, NCH = Cfg::NCH;
@@ -156,6 +160,7 @@ conv_s2d_kernel(SlotArgs sa, int64_t off_w, LayerEpi epi, const void* __restrict
     __shared__ __align__(16) float s_bias[COUT], s_mean[COUT], s_inv[COUT], s_gamma[COUT], s_beta[COUT];   // per-channel epilogue
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    pdl_trigger();                                               // common.cuh: the next kernel of the tick may be scheduled
 #ifdef DNE_S2D_TRACE
     constexpr int TRL = IN_U8 ? 0 : (KS == 4 ? 1 : 2);
 #endif
@@ -197,7 +202,7 @@ conv_s2d_kernel(SlotArgs sa, int64_t off_w, LayerEpi epi, const void* __restrict
         const uint64_t dA0 = smem_desc(sA, Cfg::LBO_A, 128), dB0 = smem_desc(sB, Cfg::LBO_B, 128);
         uint32_t cb = 0, it = 0;
         for (int slot = blockIdx.x; slot < n_slots; slot += gridDim.x) {
-            if (!slot_active(sa, slot)) continue;
+            if (!slot_active(sa, slot / vdiv)) continue;
             const uint32_t buf = it & 1;
             mbar_wait(&acc_empty[buf], ((it >> 1) & 1) ^ 1);     // the epilogue has drained this accumulator buffer
             fence_after_thread_sync();
@@ -239,14 +244,16 @@ conv_s2d_kernel(SlotArgs sa, int64_t off_w, LayerEpi epi, const void* __restrict
         // ================= image producer (TMA): the member's image, one channel-octet group per bulk copy; =================
         // ================= first layer: the member's raw uint8 frame (double buffered)                      =================
         if (lane == 0) {
+            pdl_wait();                                          // the image / frame is written by the previous kernel of the tick
             uint32_t it = 0;
             for (int slot = blockIdx.x; slot < n_slots; slot += gridDim.x) {
-                if (!slot_active(sa, slot)) continue;
+                if (!slot_active(sa, slot / vdiv)) continue;
                 if (IN_U8) {
                     const uint32_t fb = it & 1;
                     mbar_wait(&frame_empty[fb], ((it >> 1) & 1) ^ 1);
                     mbar_arrive_expect_tx(&frame_full[fb], S2D_FRAME_BYTES);
-                    bulk_g2s(gFrame + fb * S2D_FRAME_STRIDE, (const uint8_t*)in_base + slot * in_slot_stride, S2D_FRAME_BYTES,
+                    const int fslot = in_mod > 0 ? slot % in_mod : slot;
+                    bulk_g2s(gFrame + fb * S2D_FRAME_STRIDE, (const uint8_t*)in_base + fslot * in_slot_stride, S2D_FRAME_BYTES,
                              &frame_full[fb]);
                 } else {
                     const uint8_t* src = (const uint8_t*)((const float*)in_base + slot * in_slot_stride);
@@ -264,9 +271,10 @@ conv_s2d_kernel(SlotArgs sa, int64_t off_w, LayerEpi epi, const void* __restrict
         if (lane == 0) {
             uint32_t cb = 0;
             for (int slot = blockIdx.x; slot < n_slots; slot += gridDim.x) {
-                if (!slot_active(sa, slot)) continue;
-                const float* th = slot_theta(sa, slot) + off_w;
-                const float* nz = sa.noise + sa.noise_idx[slot] + off_w;
+                const int ms = slot / vdiv;
+                if (!slot_active(sa, ms)) continue;
+                const float* th = slot_theta(sa, ms) + off_w;
+                const float* nz = sa.noise + sa.noise_idx[ms] + off_w;
                 const int a_t = (int)(((uintptr_t)th >> 2) & 3), a_n = (int)(((uintptr_t)nz >> 2) & 3);
                 for (int c = 0; c < NCH; ++c, ++cb) {
                     const int g = c / NCPG, tc = c - g * NCPG;
@@ -307,11 +315,12 @@ conv_s2d_kernel(SlotArgs sa, int64_t off_w, LayerEpi epi, const void* __restrict
         const int kq0 = tg / COUT;
         uint32_t it = 0;
         for (int slot = blockIdx.x; slot < n_slots; slot += gridDim.x) {
-            if (!slot_active(sa, slot)) continue;
-            const float* th = slot_theta(sa, slot) + off_w;
-            const float* nz = sa.noise + sa.noise_idx[slot] + off_w;
+            const int ms = slot / vdiv;
+            if (!slot_active(sa, ms)) continue;
+            const float* th = slot_theta(sa, ms) + off_w;
+            const float* nz = sa.noise + sa.noise_idx[ms] + off_w;
             const int a_t = (int)(((uintptr_t)th >> 2) & 3), a_n = (int)(((uintptr_t)nz >> 2) & 3);
-            const float s = sa.scale[slot];
+            const float s = sa.scale[ms];
             if (IN_U8) mbar_wait(&frame_full[it & 1], (it >> 1) & 1);
             for (int c = grp; c < NCH; c += NGRP) {
                 const int g = c / NCPG;
@@ -389,13 +398,15 @@ conv_s2d_kernel(SlotArgs sa, int64_t off_w, LayerEpi epi, const void* __restrict
         const int act = epi.act;
         const bool bn = epi.bn != DNE_BN_NONE;
         uint32_t it = 0;
+        pdl_wait();                                              // before the first global write (the zero padding below)
         for (int slot = blockIdx.x; slot < n_slots; slot += gridDim.x) {
-            if (!slot_active(sa, slot)) continue;
-            const float* th = slot_theta(sa, slot);
-            const int64_t idx = sa.noise_idx[slot];
-            const float s = sa.scale[slot];
+            const int ms = slot / vdiv;
+            if (!slot_active(sa, ms)) continue;
+            const float* th = slot_theta(sa, ms);
+            const int64_t idx = sa.noise_idx[ms];
+            const float s = sa.scale[ms];
             for (int c = et; c < COUT; c += S2D_EPI_THREADS) {
-                const ChanEpi ce = make_chan_epi(sa, epi, slot, COUT, c, th, idx, s);
+                const ChanEpi ce = make_chan_epi(sa, epi, ms, COUT, c, th, idx, s);
                 s_bias[c] = ce.bias; s_mean[c] = ce.mean; s_inv[c] = ce.inv; s_gamma[c] = ce.gamma; s_beta[c] = ce.beta;
             }
             float* outp = so.base + slot * so.slot_stride;
@@ -494,7 +505,7 @@ conv_s2d_kernel(SlotArgs sa, int64_t off_w, LayerEpi epi, const void* __restrict
 
 template <int CIN, int COUT, int KS, int S, int HIN, int HOUT, int PAD, bool IN_U8>
 int launch_s2d(const SlotArgs& sa, const dne_layer_desc& L, const LayerEpi& epi, const void* in, int64_t in_slot_stride,
-               const S2dOut& so, int n_slots, int sm_count, cudaStream_t st) {
+               const S2dOut& so, int n_slots, int sm_count, cudaStream_t st, int vdiv, int in_mod) {
     using Cfg = S2dCfg<CIN, COUT, KS, S, HIN, HOUT, PAD, IN_U8>;
     auto kern = conv_s2d_kernel<CIN, COUT, KS, S, HIN, HOUT, PAD, IN_U8>;
     int dev = 0;
@@ -506,7 +517,11 @@ int launch_s2d(const SlotArgs& sa, const dne_layer_desc& L, const LayerEpi& epi,
         attr_done[dev] = true;
     }
     const int grid = n_slots < sm_count ? n_slots : sm_count;
-    kern<<<grid, S2D_THREADS, Cfg::SMEM_BYTES, st>>>(sa, L.off_w, epi, in, in_slot_stride, so, n_slots);
+    // the first layer follows host copies / the previous tick's graph: launched fully serialized.  The weight producer and
+    // the converter warps of the later layers never wait: theta and the noise table are not written inside a tick.
+    if (dne_launch_chain(kern, dim3(grid), dim3(S2D_THREADS), (size_t)Cfg::SMEM_BYTES, st, !IN_U8, sa, (int64_t)L.off_w, epi, in,
+                         in_slot_stride, so, n_slots, vdiv, in_mod) != cudaSuccess)
+        return DNE_ERR_CUDA;
     DNE_LAUNCHED(1);
     return 0;
 }
@@ -532,10 +547,16 @@ size_t dne_s2d_image_bytes(const dne_layer_desc& L) {
     return (size_t)g.IMG_BYTES;
 }
 
+// Geometry of layer L's input image for an external writer (vbn_image_kernel): S, PADB, W, PIXP, HP = W * S.
+void dne_s2d_image_geom(const dne_layer_desc& L, int* nS, int* nPADB, int* nW, int* nPIXP, int* nHP) {
+    const S2dGeom g = s2d_geom(L.cin, L.ksize, L.stride, L.hin, L.hout, L.pad, false);
+    *nS = g.S; *nPADB = g.PADB; *nW = g.W; *nPIXP = g.PIXP; *nHP = g.W * g.S;
+}
+
 // next: the following conv layer if it consumes an image (nullptr: write NHWC floats).
 int dne_launch_conv_layer_s2d(const SlotArgs& sa, const dne_layer_desc& L, const LayerEpi& epi, bool in_u8, const void* in,
                               int64_t in_slot_stride, float* out, int64_t out_slot_stride, const dne_layer_desc* next,
-                              int n_slots, int sm_count, cudaStream_t st, float* xc) {
+                              int n_slots, int sm_count, cudaStream_t st, float* xc, int vdiv, int in_mod) {
     S2dOut so;
     so.xc = next ? nullptr : xc;
     so.xc_ko = (L.hout * L.hout * L.cout) / 8;
@@ -547,7 +568,7 @@ int dne_launch_conv_layer_s2d(const SlotArgs& sa, const dne_layer_desc& L, const
         const S2dGeom g = s2d_geom(next->cin, next->ksize, next->stride, next->hin, next->hout, next->pad, false);
         so.nS = g.S; so.nPADB = g.PADB; so.nW = g.W; so.nPIXP = g.PIXP; so.nHP = g.W * g.S;
     }
-#define ARGS sa, L, epi, in, in_slot_stride, so, n_slots, sm_count, st
+#define ARGS sa, L, epi, in, in_slot_stride, so, n_slots, sm_count, st, (vdiv < 1 ? 1 : vdiv), in_mod
     if (in_u8 && shape_is(L, 4, 32, 8, 4, 84, 21, 2)) return launch_s2d<4, 32, 8, 4, 84, 21, 2, true>(ARGS);
     if (in_u8 && shape_is(L, 4, 16, 8, 4, 84, 21, 2)) return launch_s2d<4, 16, 8, 4, 84, 21, 2, true>(ARGS);
     if (!in_u8 && shape_is(L, 32, 64, 4, 2, 21, 11, 1)) return launch_s2d<32, 64, 4, 2, 21, 11, 1, false>(ARGS);

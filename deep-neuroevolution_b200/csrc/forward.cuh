@@ -28,11 +28,15 @@ struct GemvSrc {
 };
 
 extern int g_dne_gemv_bulk;
+extern int g_dne_fold_theta;
 extern int g_dne_gemv_ctas_per_sm;
 // TMA-bulk-copy pipelined variant of the noise GEMV (gemv_bulk.cu).  Returns DNE_ERR_UNSUP if the shape is not covered.
+int dne_launch_member_gemm_tc(const SlotArgs& sa, int64_t off_w, int64_t off_b, const float* X, int64_t x_slot_stride, int M,
+                              int K, int N, float* out, int64_t out_slot_stride, int n_slots, cudaStream_t st);
 int dne_launch_gemv_bulk(const SlotArgs& sa, const GemvSrc& src, int G, const float* X, int64_t x_slot_stride, int K,
                          int N, int rows_per_chunk, int n_chunks, int n_slots, float* part, int sm_count,
-                         cudaStream_t st);
+                         cudaStream_t st, const float* fold_theta = nullptr, int fold_n_split = 0);
+bool dne_gemv_bulk_can_fold(int G, int N, int n_chunks, int n_split);
 
 struct DensePlan {
     bool decomposed;
@@ -94,4 +98,5 @@ bool dne_s2d_supported(const dne_layer_desc& L, bool in_u8);
 size_t dne_s2d_image_bytes(const dne_layer_desc& L);
 int dne_launch_conv_layer_s2d(const SlotArgs& sa, const dne_layer_desc& L, const LayerEpi& epi, bool in_u8, const void* in,
                               int64_t in_slot_stride, float* out, int64_t out_slot_stride, const dne_layer_desc* next,
-                              int n_slots, int sm_count, cudaStream_t st, float* xc = nullptr);
+                              int n_slots, int sm_count, cudaStream_t st, float* xc = nullptr, int vdiv = 1, int in_mod = 0);
+void dne_s2d_image_geom(const dne_layer_desc& L, int* nS, int* nPADB, int* nW, int* nPIXP, int* nHP);

@@ -379,7 +379,8 @@ dense_combine_kernel(SlotArgs sa, LayerEpi epi, int n_slots, int N, int G, const
     const float s = sa.scale[slot];
     const float* th = slot_theta(sa, slot);
     const ChanEpi ce = make_chan_epi(sa, epi, slot, N, n, th, sa.noise_idx[slot], s);
-    out[(int64_t)slot * out_slot_stride + n] = ce.apply(fmaf(s, yn, yt));
+    // n_split < 0: the GEMV folded s * (noise partial) + theta partials into part_noise (gemv_bulk.cu)
+    out[(int64_t)slot * out_slot_stride + n] = ce.apply(n_split < 0 ? yn : fmaf(s, yn, yt));
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -456,7 +457,7 @@ dense_combine_head_kernel(SlotArgs sa, LayerEpi epi1, int n_slots, int N1, int G
                           int64_t off_w2, LayerEpi epi2, int N2, float* __restrict__ out, int64_t out_slot_stride,
                           int32_t* __restrict__ actions) {
     const int slot = blockIdx.x;
-    if (!slot_active(sa, slot)) return;
+    if (!slot_active(sa, slot)) return;                // (an exited CTA counts as triggered / never blocks a dependent)
     __shared__ float xs[DCH_MAXK];
     __shared__ float red[DCH_THREADS];
     __shared__ float ys[DS_MAXN];
@@ -484,6 +485,7 @@ dense_combine_head_kernel(SlotArgs sa, LayerEpi epi1, int n_slots, int N1, int G
         }
     }
     // ---- phase 1: y = act(bn(sum_split Ytheta + s * sum_chunk Ynoise + bias))  (dense_combine_kernel) ----
+    pdl_wait();                                        // common.cuh: the partial sums come from the previous kernels of the tick
     // partial sums: DCH_B predicated loads in flight, added in index order (same order as a sequential loop)
     auto sum_strided = [](const float* p, int64_t stride, int count) {
         float acc = 0.0f;
@@ -505,9 +507,9 @@ dense_combine_head_kernel(SlotArgs sa, LayerEpi epi1, int n_slots, int N1, int G
         else { pt = part_theta + (((int64_t)(slot / Gt) * n_split) * Gt + (slot % Gt)) * N1 + n; pt_stride = (int64_t)Gt * N1; }
         const int group = slot / G, g = slot % G;
         const float* pn = part_noise + (((int64_t)group * n_chunks) * G + g) * N1 + n;
-        const float yt = sum_strided(pt, pt_stride, n_split);
+        const float yt = sum_strided(pt, pt_stride, n_split);          // n_split < 0 (folded into the noise partials): no loads
         const float yn = sum_strided(pn, (int64_t)G * N1, n_chunks);
-        const float y = ce.apply(fmaf(s, yn, yt));
+        const float y = ce.apply(n_split < 0 ? yn : fmaf(s, yn, yt));
         xs[n] = y;
         if (hidden_out) hidden_out[(int64_t)slot * hidden_stride + n] = y;
     }
@@ -754,6 +756,7 @@ int dne_launch_dense_layer(const dne_ctx* ctx, const SlotArgs& sa, const dne_lay
             dense_noise_gemv_kernel<1, 8><<<grid, threads, gemv_smem(1), st>>>(sa, ts, X, x_slot_stride, K, N,
                                                                               p.rows_per_chunk, part_theta);
     }
+    bool folded = false;
     {
         GemvSrc ns{sa.noise, sa.noise_idx, nullptr, 0, L.off_w};
         dne_ctx* mctx = const_cast<dne_ctx*>(ctx);
@@ -770,9 +773,12 @@ int dne_launch_dense_layer(const dne_ctx* ctx, const SlotArgs& sa, const dne_lay
         dim3 grid(p.n_chunks, groups);
         const bool prof = ctx->prof_on && ctx->ev_n < ctx->ev_cap;
         if (prof) cudaEventRecord(ctx->ev[2 * ctx->ev_n], st);
+        // fold the theta GEMM's split-K partials into the GEMV output (gemv_bulk.cu) when the shapes allow it
+        folded = g_dne_gemv_bulk && g_dne_fold_theta && p.Gt == 0 && dne_gemv_bulk_can_fold(p.G, N, p.n_chunks, p.n_split);
         if (g_dne_gemv_bulk && dne_launch_gemv_bulk(sa, ns, p.G, X, x_slot_stride, K, N, p.rows_per_chunk, p.n_chunks,
-                                                    n_slots, part_noise, ctx->sm_count, st) == 0) {
-        } else if (p.G == 2)
+                                                    n_slots, part_noise, ctx->sm_count, st, folded ? part_theta : nullptr,
+                                                    folded ? p.n_split : 0) == 0) {
+        } else if ((folded = false), p.G == 2)
             dense_noise_gemv_kernel<2, 8><<<grid, threads, gemv_smem(2), st>>>(sa, ns, X, x_slot_stride, K, N,
                                                                               p.rows_per_chunk, part_noise);
         else
@@ -788,12 +794,15 @@ int dne_launch_dense_layer(const dne_ctx* ctx, const SlotArgs& sa, const dne_lay
         }
     }
     if (head) {          // combine + output head + argmax in one kernel (the hidden vector stays in shared memory)
-        dense_combine_head_kernel<<<n_slots, DCH_THREADS, 0, st>>>(
-            sa, epi, n_slots, N, p.G, part_theta, p.n_split, p.Gt, part_noise, p.n_chunks, out, out_slot_stride,
-            head->L->off_w, head->epi, head->L->cout, head->out, head->out_slot_stride, head->actions);
+        // PDL: the head's weight loads (theta / noise, not written inside a tick) go out before its pdl_wait()
+        if (dne_launch_chain(dense_combine_head_kernel, dim3(n_slots), dim3(DCH_THREADS), 0, st, true, sa, epi, n_slots, N, p.G,
+                             (const float*)part_theta, folded ? -1 : p.n_split, p.Gt, (const float*)part_noise, p.n_chunks, out, out_slot_stride,
+                             (int64_t)head->L->off_w, head->epi, (int)head->L->cout, head->out, head->out_slot_stride,
+                             head->actions) != cudaSuccess)
+            return DNE_ERR_CUDA;
     } else {
         dim3 grid((N + 255) / 256, n_slots);
-        dense_combine_kernel<<<grid, 256, 0, st>>>(sa, epi, n_slots, N, p.G, part_theta, p.n_split, p.Gt, part_noise,
+        dense_combine_kernel<<<grid, 256, 0, st>>>(sa, epi, n_slots, N, p.G, part_theta, folded ? -1 : p.n_split, p.Gt, part_noise,
                                                   p.n_chunks, out, out_slot_stride);
     }
     DNE_LAUNCHED(3);

@@ -30,12 +30,19 @@ constexpr int GB_THREADS = GB_CONSUMERS + 32;      // + one producer warp
 constexpr int GB_STAGES = 8;                       // maximum ring depth (barrier arrays); the launch picks n_stages <= this
 constexpr int GB_STAGE_BYTES = 16384;
 constexpr int GB_RPR = 4;                          // rows per reader per stage: (16384/4N) / (256/(N/4)) = 4 for every N
+constexpr int GB_FOLD_O = 4, GB_FOLD_S = 3;         // fold: outputs per consumer thread (G*N <= 1024), theta splits per chunk
 constexpr int GB_MAX_ROWS = 512;                   // rows per work item (x staging buffer)
 
 template <int G>
 __global__ void __launch_bounds__(GB_THREADS)
 gemv_bulk_kernel(SlotArgs sa, GemvSrc src, const float* __restrict__ X, int64_t x_slot_stride, int K, int N,
-                 int rows_per_chunk, int n_chunks, int n_groups, float* __restrict__ part, int n_stages, int pf_dist) {
+                 int rows_per_chunk, int n_chunks, int n_groups, float* __restrict__ part, int n_stages, int pf_dist,
+                 const float* __restrict__ tpart, int t_split, int n_slots) {
+    // tpart != nullptr ("fold"): the shared-theta GEMM's split-K partials [t_split][n_slots][N] are folded into this
+    // kernel's output, part[group][chunk][g][n] = s_g * (noise partial of the chunk) + sum_{j = chunk (mod n_chunks)} tpart[j]:
+    // the combine kernel then adds n_chunks values per output instead of n_chunks + t_split (its latency-bound L2 round
+    // trips were 5 of 7 for the theta partials).  The <= GB_FOLD_S loads per output are issued at the top of the item and
+    // consumed after its last stage.  Fixed summation order: deterministic.
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
     float* stage_base = reinterpret_cast<float*>(smem);
@@ -48,6 +55,7 @@ gemv_bulk_kernel(SlotArgs sa, GemvSrc src, const float* __restrict__ X, int64_t 
     const int RW = GB_CONSUMERS / NQ;                  // row readers per stage
     const int RB = GB_RPR * RW;                        // rows per stage
     const int n_items = n_groups * n_chunks;
+    pdl_trigger();                                     // common.cuh: PDL chain of the tick
 
     if (tid == 0) {
         for (int s = 0; s < n_stages; ++s) {
@@ -116,6 +124,8 @@ gemv_bulk_kernel(SlotArgs sa, GemvSrc src, const float* __restrict__ X, int64_t 
     }
 
     // ===================== consumer warps =====================
+    // (the producer above streams weight rows -- written before the tick -- without waiting; X and part need the chain)
+    pdl_wait();
     const int t = tid % NQ, rw = tid / NQ;
     const int red_ld = N + 4;
     uint32_t it = 0;
@@ -126,6 +136,20 @@ gemv_bulk_kernel(SlotArgs sa, GemvSrc src, const float* __restrict__ X, int64_t 
         int k_beg, rows, a;
         const float* base = item_base(item, k_beg, rows, a);
 
+        float tv[GB_FOLD_O][GB_FOLD_S];
+        if (tpart) {
+#pragma unroll
+            for (int o = 0; o < GB_FOLD_O; ++o) {
+                const int i = tid + o * GB_CONSUMERS;
+                const int g = i / N, n = i - g * N;
+                const bool ok = i < G * N && slot0 + g < n_slots;
+#pragma unroll
+                for (int k = 0; k < GB_FOLD_S; ++k) {
+                    const int j = chunk + k * n_chunks;
+                    tv[o][k] = (ok && j < t_split) ? __ldcg(tpart + ((int64_t)j * n_slots + slot0 + g) * N + n) : 0.0f;
+                }
+            }
+        }
         // stage x_g[k_beg-1 .. k_beg+rows) (the previous item's readers are past their last xs read: barrier C below)
         for (int i = tid; i < G * (rows + 1); i += GB_CONSUMERS) {
             const int g = i / (rows + 1), r = i % (rows + 1);
@@ -232,19 +256,40 @@ gemv_bulk_kernel(SlotArgs sa, GemvSrc src, const float* __restrict__ X, int64_t 
         }
         named_bar_sync(1, GB_CONSUMERS);                                   // barrier B
         float* out = part + ((int64_t)group * n_chunks + chunk) * G * N;
-        for (int i = tid; i < G * N; i += GB_CONSUMERS) {
-            const int g = i / N, n = i % N;
-            float sum = 0.0f;
-            for (int w = 0; w < RW; ++w) sum += red[(w * G + g) * red_ld + n];
-            out[i] = sum;
+        if (tpart) {
+#pragma unroll
+            for (int o = 0; o < GB_FOLD_O; ++o) {
+                const int i = tid + o * GB_CONSUMERS;
+                if (i < G * N) {
+                    const int g = i / N, n = i - g * N;
+                    float sum = 0.0f;
+                    for (int w = 0; w < RW; ++w) sum += red[(w * G + g) * red_ld + n];
+                    float ts = tv[o][0];
+#pragma unroll
+                    for (int k = 1; k < GB_FOLD_S; ++k) ts += tv[o][k];
+                    out[i] = fmaf(slot0 + g < n_slots ? sa.scale[slot0 + g] : 0.0f, sum, ts);
+                }
+            }
+        } else {
+            for (int i = tid; i < G * N; i += GB_CONSUMERS) {
+                const int g = i / N, n = i % N;
+                float sum = 0.0f;
+                for (int w = 0; w < RW; ++w) sum += red[(w * G + g) * red_ld + n];
+                out[i] = sum;
+            }
         }
         named_bar_sync(1, GB_CONSUMERS);                                   // barrier C: red[] and xs[] reusable
     }
 }
 
+bool dne_gemv_bulk_can_fold(int G, int N, int n_chunks, int n_split) {
+    return G * N <= GB_FOLD_O * GB_CONSUMERS && n_split >= 1 && n_split <= GB_FOLD_S * n_chunks;
+}
+
 int dne_launch_gemv_bulk(const SlotArgs& sa, const GemvSrc& src, int G, const float* X, int64_t x_slot_stride, int K,
                          int N, int rows_per_chunk, int n_chunks, int n_slots, float* part, int sm_count,
-                         cudaStream_t st) {
+                         cudaStream_t st, const float* fold_theta, int fold_n_split) {
+    if (fold_theta && !dne_gemv_bulk_can_fold(G, N, n_chunks, fold_n_split)) return DNE_ERR_UNSUP;
     // shape cover: 4 | N, N/4 divides 256, one stage = GB_RPR rows per reader
     if (N % 4 != 0 || N * 4 > GB_STAGE_BYTES || (GB_CONSUMERS % (N / 4)) != 0) return DNE_ERR_UNSUP;
     const int RW = GB_CONSUMERS / (N / 4);
@@ -267,8 +312,9 @@ int dne_launch_gemv_bulk(const SlotArgs& sa, const GemvSrc& src, int G, const fl
                 return DNE_ERR_CUDA;
             attr_done[2] = true;
         }
-        gemv_bulk_kernel<2><<<grid, GB_THREADS, smem, st>>>(sa, src, X, x_slot_stride, K, N, rows_per_chunk, n_chunks,
-                                                           n_groups, part, n_stages, g_dne_gemv_prefetch);
+        if (dne_launch_chain(gemv_bulk_kernel<2>, dim3(grid), dim3(GB_THREADS), smem, st, true, sa, src, X, x_slot_stride, K, N,
+                             rows_per_chunk, n_chunks, n_groups, part, n_stages, g_dne_gemv_prefetch, fold_theta, fold_n_split, n_slots) != cudaSuccess)
+            return DNE_ERR_CUDA;
     } else {
         if (!attr_done[1]) {
             cudaFuncSetAttribute(gemv_bulk_kernel<1>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
@@ -276,8 +322,9 @@ int dne_launch_gemv_bulk(const SlotArgs& sa, const GemvSrc& src, int G, const fl
                 return DNE_ERR_CUDA;
             attr_done[1] = true;
         }
-        gemv_bulk_kernel<1><<<grid, GB_THREADS, smem, st>>>(sa, src, X, x_slot_stride, K, N, rows_per_chunk, n_chunks,
-                                                           n_groups, part, n_stages, g_dne_gemv_prefetch);
+        if (dne_launch_chain(gemv_bulk_kernel<1>, dim3(grid), dim3(GB_THREADS), smem, st, true, sa, src, X, x_slot_stride, K, N,
+                             rows_per_chunk, n_chunks, n_groups, part, n_stages, g_dne_gemv_prefetch, fold_theta, fold_n_split, n_slots) != cudaSuccess)
+            return DNE_ERR_CUDA;
     }
     return 0;
 }

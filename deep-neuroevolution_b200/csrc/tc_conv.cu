@@ -479,3 +479,154 @@ int dne_launch_theta_gemm_tc(const float* X, int M, int K, int N, const float* W
     theta_gemm_tc_kernel<<<grid, TG_THREADS, TG_SMEM_BYTES, st>>>(X, M, K, N, W, k_per_split, part);
     return 0;
 }
+
+// =====================================================================================================
+// Per-member dense layer of the virtual-batch-norm reference pass on the tensor cores (policies.py:322-328,399; the fc
+// of ESAtariPolicy / ModelVirtualBN): out[slot][m][n] = sum_k X[slot][m][k] * fl(theta_w + fl(s*noise))[k][n] + bias_n
+// for the M = n_ref reference rows of every member.  Same tile engine as theta_gemm_tc_kernel (CTA tile 128 x 128,
+// 3xTF32, thread-staged operands, two smem stages) with blockIdx.z = member: the B operand is the member's PERTURBED
+// weight matrix, formed from the theta rows and the member's noise rows while staging; the whole K range in one CTA.
+// =====================================================================================================
+__global__ void __launch_bounds__(TG_THREADS)
+member_gemm_tc_kernel(SlotArgs sa, int64_t off_w, int64_t off_b, const float* __restrict__ X, int64_t x_slot_stride, int M,
+                      int K, int N, float* __restrict__ out, int64_t out_slot_stride) {
+    const int slot = blockIdx.z;
+    if (!slot_active(sa, slot)) return;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
+    __shared__ uint64_t bars[2];
+    __shared__ uint32_t tmem_base_s;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int m0 = blockIdx.y * TG_BM, n0 = blockIdx.x * TG_BN;
+    const int nchunk = (K + TG_KC - 1) / TG_KC;
+    const float* th = slot_theta(sa, slot);
+    const int64_t idx = sa.noise_idx[slot];
+    const float s = sa.scale[slot];
+    const float* tw = th + off_w;
+    const float* nz = sa.noise + idx + off_w;
+    const float* x = X + (int64_t)slot * x_slot_stride;
+
+    if (warp == 0) tmem_alloc(&tmem_base_s, 128);
+    if (tid == 32) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        fence_mbar_init();
+    }
+    fence_before_thread_sync();
+    __syncthreads();
+    fence_after_thread_sync();
+    const uint32_t tmem_base = tmem_base_s;
+    constexpr uint32_t IDESC = idesc_tf32(128, TG_BN);
+
+    float4 rawA[2];
+    float rawB[2][4];
+    auto load_chunk = [&](int c) {
+        const int k0 = c * TG_KC;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const int u = tid + i * TG_THREADS;
+            const int r = u % TG_BM, q = u / TG_BM;
+            const int m = m0 + r, k = k0 + 4 * q;
+            rawA[i] = (m < M && k < K) ? *reinterpret_cast<const float4*>(x + (int64_t)m * K + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+            const int n = n0 + (u % TG_BN), kb = k0 + 4 * (u / TG_BN);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int64_t f = (int64_t)(kb + j) * N + n;
+                rawB[i][j] = (n < N && kb + j < K) ? perturbed(tw[f], s, nz[f]) : 0.0f;
+            }
+        }
+    };
+    load_chunk(0);
+    for (int c = 0; c < nchunk; ++c) {
+        const int st = c & 1;
+        if (c >= 2) mbar_wait(&bars[st], ((c >> 1) - 1) & 1);
+        const uint32_t sA_hi = smem_u32(smem) + st * TG_STAGE_BYTES, sA_lo = sA_hi + TG_A_BYTES, sB_hi = sA_lo + TG_A_BYTES,
+                       sB_lo = sB_hi + TG_B_BYTES;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const int u = tid + i * TG_THREADS;
+            float4 hi, lo;
+            split_tf32_fast(rawA[i].x, hi.x, lo.x);
+            split_tf32_fast(rawA[i].y, hi.y, lo.y);
+            split_tf32_fast(rawA[i].z, hi.z, lo.z);
+            split_tf32_fast(rawA[i].w, hi.w, lo.w);
+            sts128(sA_hi + u * 16, hi);
+            sts128(sA_lo + u * 16, lo);
+            split_tf32_fast(rawB[i][0], hi.x, lo.x);
+            split_tf32_fast(rawB[i][1], hi.y, lo.y);
+            split_tf32_fast(rawB[i][2], hi.z, lo.z);
+            split_tf32_fast(rawB[i][3], hi.w, lo.w);
+            sts128(sB_hi + u * 16, hi);
+            sts128(sB_lo + u * 16, lo);
+        }
+        if (c + 1 < nchunk) load_chunk(c + 1);
+        fence_proxy_async_smem();
+        __syncthreads();
+        if (warp == 0) {
+            fence_after_thread_sync();
+            const uint64_t dA = smem_desc(smem_u32(smem) + st * TG_STAGE_BYTES, TG_A_PLANE, 128);
+            const uint64_t dB = smem_desc(smem_u32(smem) + st * TG_STAGE_BYTES + 2 * TG_A_BYTES, TG_B_PLANE, 128);
+            if (elect_one()) {
+#pragma unroll
+                for (int k8 = 0; k8 < TG_KC / 8; ++k8) {
+                    const uint64_t dAh = dA + (uint64_t)((2 * k8 * TG_A_PLANE) >> 4), dBh = dB + (uint64_t)((2 * k8 * TG_B_PLANE) >> 4);
+                    mma_tf32(tmem_base, dAh, dBh, IDESC, (c | k8) != 0);
+                    mma_tf32(tmem_base, dAh + (uint64_t)(TG_A_BYTES >> 4), dBh, IDESC, 1);
+                    mma_tf32(tmem_base, dAh, dBh + (uint64_t)(TG_B_BYTES >> 4), IDESC, 1);
+                }
+                mma_commit(&bars[st]);
+            }
+            __syncwarp();
+        }
+    }
+    mbar_wait(&bars[(nchunk - 1) & 1], ((nchunk - 1) >> 1) & 1);
+    fence_after_thread_sync();
+    float* o = out + (int64_t)slot * out_slot_stride;
+    const int lg = warp & 3, ch = warp >> 2;
+    const int m = m0 + lg * 32 + lane;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int nc = ch * 64 + j * 16;
+        float v[16];
+        tmem_ld16(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)nc, v);
+#pragma unroll
+        for (int xx = 0; xx < 16; ++xx) {
+            const int n = n0 + nc + xx;
+            const float bias = (off_b >= 0 && n < N) ? perturbed(th[off_b + n], s, sa.noise[idx + off_b + n]) : 0.0f;
+            v[xx] += bias;
+        }
+        if (m < M) {
+#pragma unroll
+            for (int xx = 0; xx < 16; xx += 4) {
+                const int n = n0 + nc + xx;
+                if (n + 3 < N) *reinterpret_cast<float4*>(o + (int64_t)m * N + n) = make_float4(v[xx], v[xx + 1], v[xx + 2], v[xx + 3]);
+                else
+                    for (int y = 0; y < 4; ++y)
+                        if (n + y < N) o[(int64_t)m * N + n + y] = v[xx + y];
+            }
+        }
+    }
+    fence_before_thread_sync();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_base, 128);
+}
+
+// returns 0 on launch, DNE_ERR_UNSUP if the shape is not covered (caller falls back to the SIMT member GEMM)
+int dne_launch_member_gemm_tc(const SlotArgs& sa, int64_t off_w, int64_t off_b, const float* X, int64_t x_slot_stride, int M,
+                              int K, int N, float* out, int64_t out_slot_stride, int n_slots, cudaStream_t st) {
+    if (K % 4 != 0 || N % 4 != 0 || K < TG_KC || (x_slot_stride & 3) || (out_slot_stride & 3) || (((uintptr_t)X | (uintptr_t)out) & 15))
+        return DNE_ERR_UNSUP;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    static bool attr_done_dev[64] = {};
+    bool& attr_done = attr_done_dev[dev < 64 ? dev : 63];
+    if (!attr_done) {
+        cudaFuncSetAttribute(member_gemm_tc_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        if (cudaFuncSetAttribute(member_gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TG_SMEM_BYTES) != cudaSuccess)
+            return DNE_ERR_CUDA;
+        attr_done = true;
+    }
+    dim3 grid((N + TG_BN - 1) / TG_BN, (M + TG_BM - 1) / TG_BM, n_slots);
+    member_gemm_tc_kernel<<<grid, TG_THREADS, TG_SMEM_BYTES, st>>>(sa, off_w, off_b, X, x_slot_stride, M, K, N, out, out_slot_stride);
+    return 0;
+}

@@ -72,6 +72,7 @@ theta_gemm_tma_kernel(const float* __restrict__ Xc, const float* __restrict__ Wc
     const int nc = max(0, c1 - c0);
     constexpr int TCOLS = MT * 256;
 
+    pdl_trigger();                                          // common.cuh: PDL chain of the tick
     if (warp == 0) tmem_alloc(&tmem_base_s, TCOLS);
     if (tid == 32) {
         for (int i = 0; i < TGM_STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], CL); }
@@ -84,6 +85,7 @@ theta_gemm_tma_kernel(const float* __restrict__ Xc, const float* __restrict__ Wc
     if (CL > 1) cluster_sync_all();                         // every peer's barriers exist before anyone multicasts into it
     const uint32_t tmem_base = tmem_base_s;
     constexpr uint16_t CL_MASK = (uint16_t)((1u << CL) - 1);
+    pdl_wait();                                             // Xc is written by the previous kernel (conv3 epilogue); part is read by the next
 
     if (warp == 0) {
         // ===== TMA producer =====
@@ -229,13 +231,15 @@ static int launch_tgm(const float* Xc, const float* Wc, int M, int N, int KQ, in
     cfg.blockDim = dim3(TGM_THREADS);
     cfg.dynamicSmemBytes = SMEM;
     cfg.stream = st;
-    cudaLaunchAttribute at[1];
+    cudaLaunchAttribute at[2];
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = CL;
     at[0].val.clusterDim.y = 1;
     at[0].val.clusterDim.z = 1;
+    at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = g_dne_pdl ? 2 : 1;
     if (cudaLaunchKernelEx(&cfg, kern, Xc, Wc, M, N, KQ, cps, n_chunks, part) != cudaSuccess) return DNE_ERR_CUDA;
     DNE_LAUNCHED(1);
     return 0;

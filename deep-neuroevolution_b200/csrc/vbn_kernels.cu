@@ -8,8 +8,16 @@
 // BN'd layer take the batch mean / biased variance per channel (these become the member's "moving" statistics
 // because decay = 0), normalise, activate, continue.  This is the one sub-problem of the path with real weight
 // reuse per member (M = n_ref*441 rows per member for conv1): a dense contraction.
+//
+// r02: with conv_tc = 2 (default) the convolutions of the pass run on the shifted-window tcgen05 kernels of the tick
+// (conv_s2d.cu) over n_slots * n_ref VIRTUAL slots (virtual slot v = image v % n_ref of member v / n_ref: consecutive CTAs
+// share a member, whose weight rows stay L2-hot), writing the raw pre-normalisation output as NHWC floats; after the batch
+// statistics, vbn_image_kernel normalises + activates and writes the NEXT conv layer's space-to-depth fp16-split image
+// (the layout the tick's conv epilogue produces), and the fc runs on member_gemm_tc_kernel (tc_conv.cu).  conv_tc = 1 keeps
+// the r01 tensor-core kernels, conv_tc = 0 the fp32 SIMT referee.
 #include "common.cuh"
 #include "forward.cuh"
+#include "tc05.cuh"
 
 __device__ __forceinline__ bool v_slot_active(const SlotArgs& a, int slot) { return !a.active || a.active[slot]; }
 __device__ __forceinline__ const float* v_slot_theta(const SlotArgs& a, int slot) {
@@ -162,6 +170,72 @@ __global__ void act_inplace_kernel(float* __restrict__ y, int64_t total, int act
     if (i < total) y[i] = apply_act(y[i], act);
 }
 
+// ---- normalise + scale/shift + activation, written as the next conv layer's space-to-depth image -----------------
+// One CTA per virtual slot (member * n_ref + image).  Same arithmetic as vbn_apply_kernel; same image layout as the
+// next_img branch of the conv_s2d epilogue: img[channel-octet plane][pixel][8 x fp16], hi planes then lo planes per
+// 16-channel group, zero padding written for the pixels no output maps to.
+struct VbnImgGeom { int nS, nPADB, nW, nPIXP, nHP; };
+__global__ void __launch_bounds__(256)
+vbn_image_kernel(SlotArgs sa, const float* __restrict__ Y, int64_t y_vslot_stride, int n_ref, int HOUT, int C, int act, int bn,
+                 int64_t off_beta, int64_t off_gamma, const float* __restrict__ vbn, int vbn_len, int bn_off,
+                 float* __restrict__ img, int64_t img_vslot_stride, VbnImgGeom g) {
+    const int v = blockIdx.x, slot = v / n_ref;
+    if (!v_slot_active(sa, slot)) return;
+    __shared__ float s_mean[64], s_inv[64], s_gamma[64], s_beta[64];
+    const float* th = v_slot_theta(sa, slot);
+    const int64_t idx = sa.noise_idx[slot];
+    const float s = sa.scale[slot];
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        float mean = 0.0f, inv = 1.0f, gamma = 1.0f, beta = 0.0f;
+        if (bn != DNE_BN_NONE) {
+            const float* st = vbn + (int64_t)slot * vbn_len + bn_off;
+            mean = st[c];
+            inv = __fdiv_rn(1.0f, __fsqrt_rn(st[C + c] + 1e-3f));
+            gamma = off_gamma >= 0 ? v_perturbed(th[off_gamma + c], s, sa.noise[idx + off_gamma + c]) : 1.0f;
+            beta = v_perturbed(th[off_beta + c], s, sa.noise[idx + off_beta + c]);
+        }
+        s_mean[c] = mean; s_inv[c] = inv; s_gamma[c] = gamma; s_beta[c] = beta;
+    }
+    __syncthreads();
+    const float* y = Y + (int64_t)v * y_vslot_stride;
+    uint4* out = reinterpret_cast<uint4*>(img + (int64_t)v * img_vslot_stride);
+    const int no = C / 8;
+    // zero padding of the image: pixels (Yp, Xp) of the padded grid that no output maps to
+    for (int b = threadIdx.x; b < g.nHP * g.nHP; b += blockDim.x) {
+        const int Yp = b / g.nHP, Xp = b - Yp * g.nHP;
+        if (Yp >= g.nPADB && Yp < g.nPADB + HOUT && Xp >= g.nPADB && Xp < g.nPADB + HOUT) continue;
+        const int pix = (Yp / g.nS) * g.nW + (Xp / g.nS), pp = (Yp % g.nS) * g.nS + (Xp % g.nS);
+        for (int q = 0; q < no; ++q) {
+            const int co = pp * no + q;
+            uint4* p = out + (size_t)((co >> 1) * 4 + (co & 1)) * g.nPIXP + pix;
+            p[0] = make_uint4(0u, 0u, 0u, 0u);
+            p[(size_t)2 * g.nPIXP] = make_uint4(0u, 0u, 0u, 0u);
+        }
+    }
+    for (int u = threadIdx.x; u < HOUT * HOUT * no; u += blockDim.x) {
+        const int m = u / no, q = u - m * no;
+        const int oy = m / HOUT, ox = m - oy * HOUT;
+        const float4 a = *reinterpret_cast<const float4*>(y + (int64_t)m * C + 8 * q);
+        const float4 b = *reinterpret_cast<const float4*>(y + (int64_t)m * C + 8 * q + 4);
+        float e[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int c = 8 * q + j;
+            float r = e[j];
+            if (bn != DNE_BN_NONE) r = (r - s_mean[c]) * s_inv[c] * s_gamma[c] + s_beta[c];
+            e[j] = apply_act(r, act);
+        }
+        uint4 hi, lo;
+        tc05::split_f16x8(e, hi, lo);
+        const int Yp = oy + g.nPADB, Xp = ox + g.nPADB;
+        const int pix = (Yp / g.nS) * g.nW + (Xp / g.nS), pp = (Yp % g.nS) * g.nS + (Xp % g.nS);
+        const int co = pp * no + q;
+        uint4* p = out + (size_t)((co >> 1) * 4 + (co & 1)) * g.nPIXP + pix;
+        p[0] = hi;
+        p[(size_t)2 * g.nPIXP] = lo;
+    }
+}
+
 static int64_t v_layer_out_elems(const dne_layer_desc& L) {
     return L.kind == DNE_CONV ? (int64_t)L.hout * L.hout * L.cout : (int64_t)L.cout;
 }
@@ -173,13 +247,39 @@ static int last_bn_layer(const dne_net_desc* net) {
     return last;
 }
 
+// Workspace layout of the pass: per layer the raw / normalised NHWC output [n_slots][n_ref][elems] and, on the s2d path,
+// the space-to-depth image of every conv layer that follows a conv layer [n_slots * n_ref][image].  The size does not depend
+// on dne_set_option("conv_tc"): the image regions are always reserved when the shapes allow the s2d path.
+struct VbnPlan {
+    bool s2d_shapes;                       // every conv layer up to the last BN layer has an s2d instantiation
+    int last;
+    size_t out_off[DNE_MAX_LAYERS], img_off[DNE_MAX_LAYERS], total;
+};
+static VbnPlan vbn_plan(const dne_net_desc* net, int n_slots, int n_ref) {
+    VbnPlan p{};
+    p.last = last_bn_layer(net);
+    p.s2d_shapes = p.last >= 0;
+    for (int l = 0; l <= p.last; ++l)
+        if (net->layers[l].kind == DNE_CONV && !dne_s2d_supported(net->layers[l], l == 0)) p.s2d_shapes = false;
+    size_t off = 0;
+    for (int l = 0; l <= p.last; ++l) {
+        p.out_off[l] = off;
+        off += align_up((size_t)n_slots * n_ref * v_layer_out_elems(net->layers[l]) * sizeof(float), 256);
+    }
+    for (int l = 1; l <= p.last; ++l) {
+        p.img_off[l] = 0;
+        if (p.s2d_shapes && net->layers[l].kind == DNE_CONV && net->layers[l - 1].kind == DNE_CONV) {
+            p.img_off[l] = off;
+            off += align_up((size_t)n_slots * n_ref * dne_s2d_image_bytes(net->layers[l]), 256);
+        }
+    }
+    p.total = off;
+    return p;
+}
+
 extern "C" int dne_vbn_ws_bytes(const dne_net_desc* net, int n_slots, int n_ref, size_t* out_bytes) {
     DNE_CHECK_ARG(net && out_bytes && n_slots >= 0 && n_ref >= 1, "bad arguments");
-    const int last = last_bn_layer(net);
-    size_t total = 0;
-    for (int l = 0; l <= last; ++l)
-        total += align_up((size_t)n_slots * n_ref * v_layer_out_elems(net->layers[l]) * sizeof(float), 256);
-    *out_bytes = total;
+    *out_bytes = vbn_plan(net, n_slots, n_ref).total;
     return DNE_OK;
 }
 
@@ -192,14 +292,14 @@ extern "C" int dne_vbn_reference_pass(dne_ctx* ctx, const dne_net_desc* net, con
     DNE_CHECK_ARG(((uintptr_t)d_theta & 15) == 0, "d_theta must be 16-byte aligned");
     DNE_CHECK_ARG(net->ob_kind == DNE_OB_ATARI_U8 && n_ref >= 1 && n_slots >= 0, "bad arguments");
     if (n_slots == 0) return DNE_OK;
-    const int last = last_bn_layer(net);
+    const VbnPlan vp = vbn_plan(net, n_slots, n_ref);
+    const int last = vp.last;
     DNE_CHECK_ARG(last >= 0 && net->vbn_len > 0, "net has no batch-norm layers");
-    size_t need = 0;
-    dne_vbn_ws_bytes(net, n_slots, n_ref, &need);
-    if (ws_bytes < need) {
-        dne_set_error("dne_vbn_reference_pass: workspace too small (%zu < %zu)", ws_bytes, need);
+    if (ws_bytes < vp.total) {
+        dne_set_error("dne_vbn_reference_pass: workspace too small (%zu < %zu)", ws_bytes, vp.total);
         return DNE_ERR_WS;
     }
+    DNE_CHECK_ARG(((uintptr_t)d_ws & 255) == 0, "d_ws must be 256-byte aligned");
     cudaStream_t st = (cudaStream_t)stream;
     SlotArgs sa;
     sa.theta = d_theta;
@@ -210,16 +310,17 @@ extern "C" int dne_vbn_reference_pass(dne_ctx* ctx, const dne_net_desc* net, con
     sa.active = d_active;
     sa.P = net->num_params;
 
+    const bool s2d = vp.s2d_shapes && g_dne_conv_tc == 2 && (int64_t)n_slots * n_ref < (int64_t)1 << 30;
+    const int n_virtual = n_slots * n_ref;
     char* ws = (char*)d_ws;
-    size_t off = 0;
-    const void* cur = d_ref;
+    const void* cur = d_ref;              // NHWC floats [n_slots][n_ref][cur_elems] (layer 0: the shared uint8 batch)
+    const float* cur_img = nullptr;       // s2d path: the layer's input as space-to-depth images [n_slots * n_ref][image]
     int64_t cur_elems = 84 * 84 * 4;      // per image
     bool cur_u8 = true;
     for (int l = 0; l <= last; ++l) {
         const dne_layer_desc& L = net->layers[l];
         const int64_t oe = v_layer_out_elems(L);
-        float* out = (float*)(ws + off);
-        off += align_up((size_t)n_slots * n_ref * oe * sizeof(float), 256);
+        float* out = (float*)(ws + vp.out_off[l]);
         const int64_t out_slot_stride = (int64_t)n_ref * oe;
         LayerEpi epi;                      // raw pre-BN output: bias only
         const int64_t pre_b = (L.bn == DNE_BN_GPU) ? -1 : L.off_b;   // ModelVirtualBN layers have no pre-normalisation bias
@@ -227,20 +328,34 @@ extern "C" int dne_vbn_reference_pass(dne_ctx* ctx, const dne_net_desc* net, con
         epi.act = DNE_ACT_NONE; epi.bn = DNE_BN_NONE; epi.bn_off = 0; epi.vbn_len = 0; epi.vbn = nullptr;
         if (L.kind == DNE_CONV) {
             DNE_CHECK_ARG((int64_t)L.hin * L.hin * L.cin == cur_elems, "conv layer input size mismatch");
-            // layer 0 reads the SHARED reference batch (slot stride 0); later layers read the member's own buffer
-            const int64_t in_slot_stride = cur_u8 ? 0 : (int64_t)n_ref * cur_elems;
-            int rc = dne_launch_conv_layer(sa, L, epi, cur_u8, cur, in_slot_stride, cur_elems, out, out_slot_stride,
-                                           oe, n_slots, n_ref, st);
+            int rc;
+            if (s2d) {
+                // n_slots * n_ref virtual slots (member = v / n_ref); layer 0 reads frame v % n_ref of the SHARED batch
+                const void* in = cur_u8 ? cur : (const void*)cur_img;
+                const int64_t in_stride = cur_u8 ? cur_elems : (int64_t)(dne_s2d_image_bytes(L) / sizeof(float));
+                DNE_CHECK_ARG(cur_u8 || cur_img, "s2d conv layer without an input image");
+                rc = dne_launch_conv_layer_s2d(sa, L, epi, cur_u8, in, in_stride, out, oe, nullptr, n_virtual, ctx->sm_count, st,
+                                               nullptr, n_ref, cur_u8 ? n_ref : 0);
+            } else {
+                // layer 0 reads the SHARED reference batch (slot stride 0); later layers read the member's own buffer
+                const int64_t in_slot_stride = cur_u8 ? 0 : (int64_t)n_ref * cur_elems;
+                rc = dne_launch_conv_layer(sa, L, epi, cur_u8, cur, in_slot_stride, cur_elems, out, out_slot_stride, oe, n_slots,
+                                           n_ref, st);
+            }
             if (rc) {
                 dne_set_error("dne_vbn_reference_pass: conv layer %d shape not compiled in", l);
                 return rc;
             }
         } else {
             DNE_CHECK_ARG(!cur_u8 && L.cin == cur_elems && L.cin % 4 == 0, "dense layer input mismatch");
-            dim3 grid((L.cout + MG_BN - 1) / MG_BN, (n_ref + MG_BM - 1) / MG_BM, n_slots);
-            member_gemm_kernel<<<grid, MG_THREADS, 0, st>>>(sa, L.off_w, pre_b, (const float*)cur,
-                                                           (int64_t)n_ref * cur_elems, n_ref, L.cin, L.cout, out,
-                                                           out_slot_stride);
+            // tensor cores (tcgen05, 3xTF32: tc_conv.cu member_gemm_tc_kernel) unless conv_tc = 0 selects the fp32 SIMT referee
+            if (!(g_dne_conv_tc && dne_launch_member_gemm_tc(sa, L.off_w, pre_b, (const float*)cur, (int64_t)n_ref * cur_elems, n_ref,
+                                                             L.cin, L.cout, out, out_slot_stride, n_slots, st) == 0)) {
+                dim3 grid((L.cout + MG_BN - 1) / MG_BN, (n_ref + MG_BM - 1) / MG_BM, n_slots);
+                member_gemm_kernel<<<grid, MG_THREADS, 0, st>>>(sa, L.off_w, pre_b, (const float*)cur,
+                                                               (int64_t)n_ref * cur_elems, n_ref, L.cin, L.cout, out,
+                                                               out_slot_stride);
+            }
             DNE_LAUNCHED(1);
         }
         DNE_LAUNCH_CHECK();
@@ -250,18 +365,33 @@ extern "C" int dne_vbn_reference_pass(dne_ctx* ctx, const dne_net_desc* net, con
             vbn_stats_kernel<<<dim3((C + 31) / 32, n_slots), 256, 0, st>>>(sa, out, out_slot_stride, rows, C, d_vbn,
                                                                           net->vbn_len, L.bn_off);
             DNE_LAUNCH_CHECK1();
-            if (l < last) {
+        }
+        cur_img = nullptr;
+        if (l < last) {
+            const bool to_image = s2d && L.kind == DNE_CONV && vp.img_off[l + 1] != 0 && C % 8 == 0 && C <= 64;
+            if (s2d && net->layers[l + 1].kind == DNE_CONV) DNE_CHECK_ARG(to_image, "s2d path: conv layer after a non-conv layer");
+            if (to_image) {
+                VbnImgGeom g;
+                dne_s2d_image_geom(net->layers[l + 1], &g.nS, &g.nPADB, &g.nW, &g.nPIXP, &g.nHP);
+                float* img = (float*)(ws + vp.img_off[l + 1]);
+                vbn_image_kernel<<<n_virtual, 256, 0, st>>>(sa, out, oe, n_ref, L.hout, C, L.act, L.bn,
+                                                           L.bn == DNE_BN_GPU ? L.off_b : L.off_beta,
+                                                           L.bn == DNE_BN_GPU ? (int64_t)-1 : L.off_gamma, d_vbn, net->vbn_len,
+                                                           L.bn_off, img, (int64_t)(dne_s2d_image_bytes(net->layers[l + 1]) / sizeof(float)), g);
+                DNE_LAUNCH_CHECK1();
+                cur_img = img;
+            } else if (L.bn != DNE_BN_NONE) {
                 const int gx = (int)((out_slot_stride + 255) / 256 < 1024 ? (out_slot_stride + 255) / 256 : 1024);
                 vbn_apply_kernel<<<dim3(gx, n_slots), 256, 0, st>>>(sa, out, out_slot_stride, out_slot_stride, C,
                                                                    L.act, L.bn == DNE_BN_GPU ? L.off_b : L.off_beta,
                                                                    L.bn == DNE_BN_GPU ? (int64_t)-1 : L.off_gamma, d_vbn,
                                                                    net->vbn_len, L.bn_off);
                 DNE_LAUNCH_CHECK1();
+            } else if (L.act != DNE_ACT_NONE) {
+                const int64_t total = (int64_t)n_slots * out_slot_stride;
+                act_inplace_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(out, total, L.act);
+                DNE_LAUNCH_CHECK1();
             }
-        } else if (L.act != DNE_ACT_NONE && l < last) {
-            const int64_t total = (int64_t)n_slots * out_slot_stride;
-            act_inplace_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(out, total, L.act);
-            DNE_LAUNCH_CHECK1();
         }
         cur = out;
         cur_elems = oe;

@@ -298,3 +298,43 @@ def test_theta_gemm_tma_vs_thread_staged_and_invalidation(ctx, host_noise):
     assert (np.abs(raw[rows] - ref).max(axis=1) <= bound).all()
     assert (np.abs(eng[rows] - ref).max(axis=1) <= bound).all()
     assert float((before - torch.from_numpy(eng).to(DEV)).abs().max()) > 1e-3       # the step really changed the outputs
+
+
+@pytest.mark.parametrize("name", ["ESAtariPolicy", "ModelVirtualBN"])
+def test_vbn_reference_pass_tensor_core_paths_match_simt(ctx, host_noise, name):
+    """The virtual-batch-norm reference pass (policies.py:322-328,399) three ways: conv_tc = 2 (shifted-window tcgen05
+    convolutions over n_slots * n_ref virtual slots + fp16-split images + tensor-core member GEMM), conv_tc = 1 (r01
+    tensor-core kernels) and conv_tc = 0 (fp32 SIMT referee): same statistics, and the tick on those statistics gives the
+    same logits.  Ragged sizes: n_ref not a multiple of anything, an inactive slot in the middle, unpaired scales."""
+    net = N.make_net(name)
+    P = net.num_params
+    rs = np.random.RandomState(77)
+    theta = (rs.randn(P) * 0.05).astype(np.float32)
+    n_slots, n_ref = 10, 21
+    idx = rs.randint(0, NOISE_COUNT - P + 1, size=n_slots).astype(np.int64)
+    scale = (0.005 * rs.randn(n_slots)).astype(np.float32)
+    active = np.ones(n_slots, dtype=np.uint8)
+    active[3] = 0
+    ref_batch = cuda(rs.randint(0, 256, size=(n_ref, 84, 84, 4)).astype(np.uint8))
+    obs = cuda(rs.randint(0, 256, size=(n_slots, 84, 84, 4)).astype(np.uint8))
+    d_theta = cuda(theta)
+    res = {}
+    try:
+        for mode in (2, 1, 0):
+            F.check(F.lib().dne_set_option(b"conv_tc", mode))
+            sf = SlotForward(ctx, net, n_slots, n_ref=n_ref)
+            sf.set_slots(idx, scale, active=active)
+            sf.vbn.fill_(float("nan"))
+            sf.vbn_reference_pass(d_theta, ref_batch, active=sf.active)
+            sf.forward(d_theta, obs, paired=False)
+            torch.cuda.synchronize()
+            res[mode] = (sf.vbn.cpu().numpy().copy(), sf.logits.cpu().numpy().copy())
+    finally:
+        F.check(F.lib().dne_set_option(b"conv_tc", 2))
+    live = active.astype(bool)
+    for mode in (2, 1):
+        vbn, logits = res[mode]
+        assert np.isnan(vbn[~live]).all()                        # inactive slots are not touched
+        assert np.isfinite(vbn[live]).all()
+        np.testing.assert_allclose(vbn[live], res[0][0][live], rtol=3e-4, atol=3e-5)
+        np.testing.assert_allclose(logits[live], res[0][1][live], rtol=0, atol=5e-4 * max(1.0, np.abs(res[0][1][live]).max()))
