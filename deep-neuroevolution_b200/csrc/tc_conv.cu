@@ -487,7 +487,7 @@ int dne_launch_theta_gemm_tc(const float* X, int M, int K, int N, const float* W
 // 3xTF32, thread-staged operands, two smem stages) with blockIdx.z = member: the B operand is the member's PERTURBED
 // weight matrix, formed from the theta rows and the member's noise rows while staging; the whole K range in one CTA.
 // =====================================================================================================
-__global__ void __launch_bounds__(TG_THREADS)
+__global__ void __launch_bounds__(TG_THREADS, 2)
 member_gemm_tc_kernel(SlotArgs sa, int64_t off_w, int64_t off_b, const float* __restrict__ X, int64_t x_slot_stride, int M,
                       int K, int N, float* __restrict__ out, int64_t out_slot_stride) {
     const int slot = blockIdx.z;
@@ -518,6 +518,11 @@ member_gemm_tc_kernel(SlotArgs sa, int64_t off_w, int64_t off_b, const float* __
     const uint32_t tmem_base = tmem_base_s;
     constexpr uint32_t IDESC = idesc_tf32(128, TG_BN);
 
+    constexpr int MG_DRAIN = 16;
+    const int lg = warp & 3, ch = warp >> 2;                     // epilogue / drain map: TMEM lane quarter, 64-column half
+    float accr[64];
+#pragma unroll
+    for (int xx = 0; xx < 64; ++xx) accr[xx] = 0.0f;
     float4 rawA[2];
     float rawB[2][4];
     auto load_chunk = [&](int c) {
@@ -570,7 +575,7 @@ member_gemm_tc_kernel(SlotArgs sa, int64_t off_w, int64_t off_b, const float* __
 #pragma unroll
                 for (int k8 = 0; k8 < TG_KC / 8; ++k8) {
                     const uint64_t dAh = dA + (uint64_t)((2 * k8 * TG_A_PLANE) >> 4), dBh = dB + (uint64_t)((2 * k8 * TG_B_PLANE) >> 4);
-                    mma_tf32(tmem_base, dAh, dBh, IDESC, (c | k8) != 0);
+                    mma_tf32(tmem_base, dAh, dBh, IDESC, ((c % MG_DRAIN) | k8) != 0);
                     mma_tf32(tmem_base, dAh + (uint64_t)(TG_A_BYTES >> 4), dBh, IDESC, 1);
                     mma_tf32(tmem_base, dAh, dBh + (uint64_t)(TG_B_BYTES >> 4), IDESC, 1);
                 }
@@ -578,17 +583,29 @@ member_gemm_tc_kernel(SlotArgs sa, int64_t off_w, int64_t off_b, const float* __
             }
             __syncwarp();
         }
+        if ((c % MG_DRAIN) == MG_DRAIN - 1 || c == nchunk - 1) {
+            // drain the TMEM accumulator into fp32 registers every MG_DRAIN chunks (K = 256): the tensor core's accumulator add
+            // is not round-to-nearest, and over K = 3872 its bias reached 4e-5 (VBN statistics are compared at 2e-5)
+            mbar_wait(&bars[st], (c >> 1) & 1);                  // every MMA up to chunk c has completed
+            fence_after_thread_sync();
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float v[16];
+                tmem_ld16(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)(ch * 64 + j * 16), v);
+#pragma unroll
+                for (int xx = 0; xx < 16; ++xx) accr[j * 16 + xx] += v[xx];
+            }
+            fence_before_thread_sync();                          // ordered before the next chunk's __syncthreads + MMA (accumulate = 0)
+        }
     }
-    mbar_wait(&bars[(nchunk - 1) & 1], ((nchunk - 1) >> 1) & 1);
-    fence_after_thread_sync();
     float* o = out + (int64_t)slot * out_slot_stride;
-    const int lg = warp & 3, ch = warp >> 2;
     const int m = m0 + lg * 32 + lane;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
         const int nc = ch * 64 + j * 16;
         float v[16];
-        tmem_ld16(tmem_base + ((uint32_t)(lg * 32) << 16) + (uint32_t)nc, v);
+#pragma unroll
+        for (int xx = 0; xx < 16; ++xx) v[xx] = accr[j * 16 + xx];
 #pragma unroll
         for (int xx = 0; xx < 16; ++xx) {
             const int n = n0 + nc + xx;

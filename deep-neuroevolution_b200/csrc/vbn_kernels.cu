@@ -144,6 +144,64 @@ vbn_stats_kernel(SlotArgs sa, const float* __restrict__ Y, int64_t y_slot_stride
     }
 }
 
+
+// ---- batch statistics, r02: coalesced, many CTAs per member ------------------------------------------------------
+// vbn_stats_partial_kernel: grid (VS_SPLIT, n_slots); CTA (sp, slot) reads a contiguous range of the member's rows as float4
+// units (thread t keeps channel quad t % (C/4): C/4 divides 256 for the policies' channel counts 16 / 32 / 64 / 256 / 512) and
+// accumulates sum and sum of squares in float64; fixed-order block reduction -> red[slot][sp][2][C] doubles.
+// vbn_stats_final_kernel: adds the VS_SPLIT partials in index order; mean = S1/rows, var = S2/rows - mean^2 in float64
+// (the two-pass form of vbn_stats_kernel, kept for C % 4 != 0, differs from it by (mean - fl(mean))^2 ~ 1e-15).
+constexpr int VS_SPLIT = 16;
+__global__ void __launch_bounds__(256)
+vbn_stats_partial_kernel(SlotArgs sa, const float* __restrict__ Y, int64_t y_slot_stride, int rows, int C,
+                         double* __restrict__ red) {
+    const int slot = blockIdx.y, sp = blockIdx.x;
+    if (!v_slot_active(sa, slot)) return;
+    const int Q = C >> 2;                                  // channel quads per row
+    const int64_t units = (int64_t)rows * Q;
+    const int64_t per = ((units + VS_SPLIT - 1) / VS_SPLIT + 255) / 256 * 256;      // multiple of 256: a thread keeps its quad
+    const int64_t u0 = (int64_t)sp * per, u1 = min(units, u0 + per);
+    const float4* y = reinterpret_cast<const float4*>(Y + (int64_t)slot * y_slot_stride);
+    double s1[4] = {0.0, 0.0, 0.0, 0.0}, s2[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int64_t u = u0 + threadIdx.x; u < u1; u += 256) {
+        const float4 v = y[u];
+        s1[0] += v.x; s1[1] += v.y; s1[2] += v.z; s1[3] += v.w;
+        s2[0] += (double)v.x * v.x; s2[1] += (double)v.y * v.y; s2[2] += (double)v.z * v.z; s2[3] += (double)v.w * v.w;
+    }
+    __shared__ double sh[256][8];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { sh[threadIdx.x][j] = s1[j]; sh[threadIdx.x][4 + j] = s2[j]; }
+    __syncthreads();
+    // thread c < C owns channel c: quad c / 4 is held by the threads t = c / 4 (mod Q)
+    for (int c = threadIdx.x; c < C; c += 256) {
+        double a = 0.0, b = 0.0;
+        for (int t = c >> 2; t < 256; t += Q) { a += sh[t][c & 3]; b += sh[t][4 + (c & 3)]; }
+        double* r = red + (((int64_t)slot * VS_SPLIT + sp) * 2) * C;
+        r[c] = a;
+        r[C + c] = b;
+    }
+}
+
+__global__ void vbn_stats_final_kernel(SlotArgs sa, const double* __restrict__ red, int rows, int C, float* __restrict__ vbn,
+                                       int vbn_len, int bn_off) {
+    const int slot = blockIdx.x;
+    if (!v_slot_active(sa, slot)) return;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        double a = 0.0, b = 0.0;
+        for (int sp = 0; sp < VS_SPLIT; ++sp) {
+            const double* r = red + (((int64_t)slot * VS_SPLIT + sp) * 2) * C;
+            a += r[c];
+            b += r[C + c];
+        }
+        const double mean = a / (double)rows;
+        double var = b / (double)rows - mean * mean;
+        if (var < 0.0) var = 0.0;
+        float* st = vbn + (int64_t)slot * vbn_len + bn_off;
+        st[c] = (float)mean;
+        st[C + c] = (float)var;
+    }
+}
+
 // ---- normalise + scale/shift + activation in place --------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 vbn_apply_kernel(SlotArgs sa, float* __restrict__ Y, int64_t y_slot_stride, int64_t elems, int C, int act,
@@ -253,7 +311,7 @@ static int last_bn_layer(const dne_net_desc* net) {
 struct VbnPlan {
     bool s2d_shapes;                       // every conv layer up to the last BN layer has an s2d instantiation
     int last;
-    size_t out_off[DNE_MAX_LAYERS], img_off[DNE_MAX_LAYERS], total;
+    size_t out_off[DNE_MAX_LAYERS], img_off[DNE_MAX_LAYERS], red_off, total;
 };
 static VbnPlan vbn_plan(const dne_net_desc* net, int n_slots, int n_ref) {
     VbnPlan p{};
@@ -273,6 +331,10 @@ static VbnPlan vbn_plan(const dne_net_desc* net, int n_slots, int n_ref) {
             off += align_up((size_t)n_slots * n_ref * dne_s2d_image_bytes(net->layers[l]), 256);
         }
     }
+    int cmax = 1;
+    for (int l = 0; l <= p.last; ++l) cmax = net->layers[l].cout > cmax ? net->layers[l].cout : cmax;
+    p.red_off = off;                                       // float64 partial sums of the statistics: [n_slots][VS_SPLIT][2][C]
+    off += align_up((size_t)n_slots * VS_SPLIT * 2 * cmax * sizeof(double), 256);
     p.total = off;
     return p;
 }
@@ -362,8 +424,15 @@ extern "C" int dne_vbn_reference_pass(dne_ctx* ctx, const dne_net_desc* net, con
         const int C = L.cout;
         const int rows = (int)(out_slot_stride / C);
         if (L.bn != DNE_BN_NONE) {
-            vbn_stats_kernel<<<dim3((C + 31) / 32, n_slots), 256, 0, st>>>(sa, out, out_slot_stride, rows, C, d_vbn,
-                                                                          net->vbn_len, L.bn_off);
+            if (C % 4 == 0 && 256 % (C / 4) == 0 && (out_slot_stride & 3) == 0 && g_dne_conv_tc != 0) {
+                double* red = (double*)(ws + vp.red_off);
+                vbn_stats_partial_kernel<<<dim3(VS_SPLIT, n_slots), 256, 0, st>>>(sa, out, out_slot_stride, rows, C, red);
+                DNE_LAUNCH_CHECK1();
+                vbn_stats_final_kernel<<<n_slots, 256, 0, st>>>(sa, red, rows, C, d_vbn, net->vbn_len, L.bn_off);
+            } else {                                        // referee (conv_tc = 0) and odd channel counts: two-pass kernel
+                vbn_stats_kernel<<<dim3((C + 31) / 32, n_slots), 256, 0, st>>>(sa, out, out_slot_stride, rows, C, d_vbn,
+                                                                              net->vbn_len, L.bn_off);
+            }
             DNE_LAUNCH_CHECK1();
         }
         cur_img = nullptr;

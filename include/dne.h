@@ -93,15 +93,18 @@ int         dne_abi_sizes(int* layer_desc_bytes, int* net_desc_bytes);
  * dne_profile_enable/read: CUDA-event timing of every launch of the dominant HBM-bound kernel
  * (dense_noise_gemv) on the stream it is launched on; read() synchronises the device. */
 long long   dne_launch_count(int reset);
-/* Runtime switches (process-wide):
- *   "conv_tc" = 1 (default): member convolutions + the shared-theta GEMM on the tensor cores (tcgen05.mma kind::tf32,
- *               3xTF32 split, TMEM accumulators); 0 selects the fp32 SIMT kernels (kept for A/B parity checks).
+/* Runtime switches (process-wide; A/B measurement and referee paths only):
+ *   "conv_tc" = 2 (default): shifted-window tcgen05 convolutions, images / weights by TMA (conv_s2d.cu), also used by the
+ *               virtual-batch-norm reference pass; 1: im2col-staged tcgen05 kind::tf32 convolutions (tc_conv.cu); 0: fp32 SIMT
+ *               kernels everywhere (the parity referee).
+ *   "theta_tma" = 1 (default): TMA-fed shared-theta GEMM when a prepared region is current (dne_theta_prepare).
+ *   "theta_mc" = 0 (default): cluster-multicast variant of it (measured slower).
+ *   "fuse_head" = 1 (default): combine + output head + argmax in one kernel.
+ *   "fold_theta" = 1 (default): the theta GEMM's split-K partials are folded into the noise GEMV's output.
+ *   "pdl" = 1 (default): the tick's kernels are chained by programmatic dependent launch (griddepcontrol).
  *   "gemv_bulk" = 1 (default): noise GEMV through the cp.async.bulk shared-memory ring; 0 = plain-LDG kernel.
- *   "conv_tc" = 2 (default): shifted-window convolutions with TMA-fed images / weights (conv_s2d.cu); 1: im2col-staged tcgen05
- *               convolutions (tc_conv.cu); 0: fp32 SIMT.  "theta_tma" = 1 (default): TMA-fed shared-theta GEMM when prepared.
- *               "fuse_head" = 1 (default): combine + output head + argmax in one kernel.
- *   "gemv_ctas_per_sm" = 1|2 (default 2), "gemv_stages" = 2..8 (default 6): persistent-grid size / ring depth of it.
- *   "gemv_prefetch" = 0..256 (default 0): L2 prefetch distance in 16 KB stages (measured slower on B200; off). */
+ *   "gemv_ctas_per_sm" = 1|2 (default 2), "gemv_stages" = 2..8 (default 6), "gemv_grid" (default 0 = no cap),
+ *   "gemv_chunk_kb" (work-item size), "gemv_prefetch" = 0..256 (default 0; L2 prefetch distance, measured slower). */
 int         dne_set_option(const char* name, int value);
 int         dne_profile_enable(dne_ctx* ctx, int on, int capacity);
 int         dne_profile_read(dne_ctx* ctx, int* n_launches, double* total_ms);
