@@ -85,6 +85,7 @@ extern "C" int dne_set_option(const char* name, int value) {
     if (strcmp(name, "gemv_prefetch") == 0 && value >= 0 && value <= 256) { extern int g_dne_gemv_prefetch; g_dne_gemv_prefetch = value; return DNE_OK; }
     if (strcmp(name, "fold_theta") == 0 && value >= 0 && value <= 1) { g_dne_fold_theta = value; return DNE_OK; }
     if (strcmp(name, "pdl") == 0 && value >= 0 && value <= 1) { g_dne_pdl = value; return DNE_OK; }
+    if (strcmp(name, "gemv_balance") == 0 && value >= 0 && value <= 1) { extern int g_dne_gemv_balance; g_dne_gemv_balance = value; return DNE_OK; }
     if (strcmp(name, "gemv_grid") == 0 && value >= 0) { extern int g_dne_gemv_grid; g_dne_gemv_grid = value; return DNE_OK; }
     if (strcmp(name, "gemv_ctas_per_sm") == 0 && value >= 1 && value <= 2) { g_dne_gemv_ctas_per_sm = value; return DNE_OK; }
     dne_set_error("dne_set_option: unknown option '%s'", name);

@@ -774,7 +774,8 @@ int dne_launch_dense_layer(const dne_ctx* ctx, const SlotArgs& sa, const dne_lay
         const bool prof = ctx->prof_on && ctx->ev_n < ctx->ev_cap;
         if (prof) cudaEventRecord(ctx->ev[2 * ctx->ev_n], st);
         // fold the theta GEMM's split-K partials into the GEMV output (gemv_bulk.cu) when the shapes allow it
-        folded = g_dne_gemv_bulk && g_dne_fold_theta && p.Gt == 0 && dne_gemv_bulk_can_fold(p.G, N, p.n_chunks, p.n_split);
+        folded = g_dne_gemv_bulk && g_dne_fold_theta && p.Gt == 0 && dne_gemv_bulk_can_fold(p.G, N, p.n_chunks, p.n_split) &&
+                 p.rows_per_chunk * N >= 192 * 1024;   // >= 768 KB items: with the 512 KB items of small tables the fold costs 0.8 us (A/B, tools/ab_tick.py)
         if (g_dne_gemv_bulk && dne_launch_gemv_bulk(sa, ns, p.G, X, x_slot_stride, K, N, p.rows_per_chunk, p.n_chunks,
                                                     n_slots, part_noise, ctx->sm_count, st, folded ? part_theta : nullptr,
                                                     folded ? p.n_split : 0) == 0) {
