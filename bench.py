@@ -200,8 +200,12 @@ def run_b200(args):
                 torch.cuda.synchronize()
             bd.append((tag, time.perf_counter()))
 
+    rollout_ev = []              # (start, end) CUDA events around the rollout part of every generation (this rank's own work)
+
     def generation_value():
         mark("start")
+        ev_a, ev_b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev_a.record()
         idx_all = np.array([noise.sample_index(idx_stream, P) for _ in range(n_pairs)], dtype=np.int64)
         my = idx_all[lo:hi]
         returns = torch.zeros(len(my), 2, device=dev)
@@ -277,6 +281,8 @@ def run_b200(args):
             mark("ticks_done")
             r = torch.cat([ret_acc[h * part:h * part + 2 * len(parts[h])] for h in range(NS)]).view(-1, 2)
             returns[w0:w0 + npw] = r
+        ev_b.record()
+        rollout_ev.append((ev_a, ev_b))
         allret = shard.all_gather_rows(returns, n_pairs)
         proc, _ = upd.centered_ranks(allret)
         g = upd.gradient(proc[lo:hi].contiguous(), torch.from_numpy(my).to(dev), denom=2 * n_pairs)
@@ -328,6 +334,15 @@ def run_b200(args):
         return float(t.item()), clocks, launches, prof
 
     ms_val, clocks, launches, prof = timed(generation_value, args.steps, args.warmup, profile=True)
+    # this rank's own rollout time per generation (before the all_gather that synchronises the ranks): rank skew shows here
+    my_roll = sum(a.elapsed_time(b) for a, b in rollout_ev[-args.steps:]) / args.steps
+    roll_t = torch.tensor([my_roll], dtype=torch.float64, device=dev)
+    roll_all = [torch.zeros_like(roll_t) for _ in range(world)]
+    if world > 1:
+        dist.all_gather(roll_all, roll_t)
+    else:
+        roll_all = [roll_t]
+    rank_rollout_ms = [round(float(t.item()), 3) for t in roll_all]
     env_steps = args.steps * args.pop * T
     value = env_steps / (ms_val / 1e3)
 
@@ -424,6 +439,7 @@ def run_b200(args):
             "parity_checked": bool(parity and parity["checked"]), "parity": parity,
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
             "noise_table_build_s": t_noise,
+            "rank_rollout_ms": rank_rollout_ms,     # per rank: device time of its rollouts per generation (ms_per_step = slowest rank + exchange + update)
         }
         _emit(line)
     if world > 1:
