@@ -71,7 +71,7 @@ class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+         "clocks_event_reasons.sw_power_cap,enforced.power.limit")
 
     def __init__(self, gpu_index=0):
         self.rows, self.proc, self.gpu = [], None, gpu_index
@@ -98,8 +98,16 @@ class ClockSampler:
         mx = [float(r[2]) for r in self.rows if len(r) >= 8 and r[2].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = sorted({names[i] for r in self.rows if len(r) >= 8 for i in range(4) if r[4 + i].lower().startswith("active")})
+        def num(x):
+            try:
+                return float(x)
+            except ValueError:
+                return None
+        pw = [num(r[3]) for r in self.rows if len(r) >= 8 and num(r[3]) is not None]
+        lim = [num(r[8]) for r in self.rows if len(r) >= 9 and num(r[8]) is not None]
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+                "reasons": reasons, "samples": len(sm), "power_w": float(np.median(pw)) if pw else None,
+                "power_limit_w": max(lim) if lim else None}
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -184,10 +192,17 @@ def run_b200(args):
     ev_ptr = [C.c_void_p(e.cuda_event) for e in phase_ev]
 
     KERNELS_PER_TICK = 6          # conv1-3, theta GEMM, noise GEMV, combine+head (LargeModel, default options)
-    USE_GRAPH = os.environ.get("DNE_BENCH_GRAPH", "1") == "1"       # r02 A/B at T=200: 639K vs 612K env-steps/s
+    # Tick launch.  Default: kernel by kernel on one stream, the six kernels AND consecutive ticks chained by programmatic
+    # dependent launch (dne_set_option("chain_ticks", 1): with device-resident observations the stream's previous
+    # kernel of a tick's first convolution is the previous tick's head) -- interleaved A/B (tools/ab_tick.py): 2-5 us per tick
+    # faster than one CUDA graph per tick, whose launch boundary is a full dependency.  DNE_BENCH_GRAPH=1 replays graphs.
+    USE_GRAPH = os.environ.get("DNE_BENCH_GRAPH", "0") == "1"
+    CHAIN = (not USE_GRAPH) and os.environ.get("DNE_BENCH_CHAIN", "1") == "1"
     if NS >= 2 and PHASED:
         USE_GRAPH = False        # the phase-event hand-off between slot tables (cross-stream events) is not captured
-    PROF_EVERY = 16 if USE_GRAPH else 1
+    if NS >= 2 and PHASED:
+        CHAIN = False
+    PROF_EVERY = 16              # every 16th tick carries the CUDA-event records around the GEMV (they break the PDL chain there)
     graphs = {}
     prof_state = {"on": False}
 
@@ -268,10 +283,10 @@ def run_b200(args):
                             g.replay()
                         tally["graph_kernels"] = tally.get("graph_kernels", 0) + KERNELS_PER_TICK
                     else:
-                        if USE_GRAPH and prof_state["on"]:
+                        if prof_state["on"] and (t % PROF_EVERY) == 0:
                             L.dne_profile_enable(ctx.handle, 2, 0)          # resume (keeps the samples taken so far)
                             tick(h, r)
-                            L.dne_profile_enable(ctx.handle, 0, 0)          # pause: graph replays carry no event records
+                            L.dne_profile_enable(ctx.handle, 0, 0)          # pause: the other ticks carry no event records
                         else:
                             tick(h, r)
                 ret_acc.add_(rew_pool[t % 64])                     # one bookkeeping op per tick, main stream
@@ -303,8 +318,7 @@ def run_b200(args):
         if profile:
             F.check(L.dne_profile_enable(ctx.handle, 1, 16384))
             prof_state["on"] = True
-            if USE_GRAPH:
-                F.check(L.dne_profile_enable(ctx.handle, 0, 0))             # paused; resumed around the un-graphed ticks
+            F.check(L.dne_profile_enable(ctx.handle, 0, 0))                 # paused; resumed around every 16th tick
         L.dne_launch_count(1)
         tally["graph_kernels"] = 0
         sampler = ClockSampler(local)
@@ -333,7 +347,12 @@ def run_b200(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item()), clocks, launches, prof
 
-    ms_val, clocks, launches, prof = timed(generation_value, args.steps, args.warmup, profile=True)
+    if CHAIN:
+        F.check(L.dne_set_option(b"chain_ticks", 1))
+    try:
+        ms_val, clocks, launches, prof = timed(generation_value, args.steps, args.warmup, profile=True)
+    finally:
+        F.check(L.dne_set_option(b"chain_ticks", 0))
     # this rank's own rollout time per generation (before the all_gather that synchronises the ranks): rank skew shows here
     my_roll = sum(a.elapsed_time(b) for a, b in rollout_ev[-args.steps:]) / args.steps
     roll_t = torch.tensor([my_roll], dtype=torch.float64, device=dev)
@@ -431,7 +450,8 @@ def run_b200(args):
                        "population": args.pop, "noise_pairs": n_pairs, "policy": "LargeModel (P=4052658, 18 actions)",
                        "env_slots_per_gpu": slots, "slot_tables": NS, "episode_len": T, "noise_table": args.noise_count,
                        "tick_launch": "CUDA graph replay (6 kernels; every 16th tick kernel by kernel for the CUDA-event GEMV timing)"
-                                      if USE_GRAPH else "kernel by kernel",
+                                      if USE_GRAPH else ("kernel by kernel, kernels and consecutive ticks chained by programmatic dependent "
+                                                         "launch (every 16th tick carries the CUDA-event GEMV timing)" if CHAIN else "kernel by kernel"),
                        "sharding": f"population over {world} rank(s); all_gather(returns)+all_reduce(g)",
                        "l2": "inputs larger than L2 (>=1 GB of noise slices streamed per tick)",
                        "step": "one generation (rollouts + update)"},

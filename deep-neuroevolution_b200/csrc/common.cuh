@@ -73,6 +73,7 @@ void dne_set_error(const char* fmt, ...);
 // which itself waited for ITS predecessor, so completion is transitive along the chain.  The launch latency and the
 // prologue of kernel i+1 overlap the tail of kernel i.  dne_set_option("pdl", 0) launches the chain fully serialized.
 extern int g_dne_pdl;
+extern int g_dne_chain_ticks;
 template <typename... KArgs, typename... Args>
 static inline cudaError_t dne_launch_chain(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool dependent,
                                            Args... args) {

@@ -519,7 +519,9 @@ int launch_s2d(const SlotArgs& sa, const dne_layer_desc& L, const LayerEpi& epi,
     const int grid = n_slots < sm_count ? n_slots : sm_count;
     // the first layer follows host copies / the previous tick's graph: launched fully serialized.  The weight producer and
     // the converter warps of the later layers never wait: theta and the noise table are not written inside a tick.
-    if (dne_launch_chain(kern, dim3(grid), dim3(S2D_THREADS), (size_t)Cfg::SMEM_BYTES, st, !IN_U8, sa, (int64_t)L.off_w, epi, in,
+    // (dne_set_option("chain_ticks", 1): the caller guarantees that the stream's previous kernel is the previous tick's head --
+    // nothing that writes theta, the noise table or the slot table -- and the first layer joins the chain too.)
+    if (dne_launch_chain(kern, dim3(grid), dim3(S2D_THREADS), (size_t)Cfg::SMEM_BYTES, st, !IN_U8 || g_dne_chain_ticks, sa, (int64_t)L.off_w, epi, in,
                          in_slot_stride, so, n_slots, vdiv, in_mod) != cudaSuccess)
         return DNE_ERR_CUDA;
     DNE_LAUNCHED(1);

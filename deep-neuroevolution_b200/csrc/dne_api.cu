@@ -5,6 +5,7 @@
 static thread_local char g_err[512] = "";
 unsigned long long g_dne_launches = 0;
 int g_dne_theta_tma = 1;     // TMA-fed shared-theta GEMM when a prepared region is current (dne_set_option("theta_tma", v))
+int g_dne_chain_ticks = 0;   // the first conv layer of a tick is a dependent launch too (dne_set_option("chain_ticks", v); see conv_s2d.cu)
 int g_dne_pdl = 1;           // programmatic dependent launch of the tick's kernel chain (common.cuh; dne_set_option("pdl", v))
 int g_dne_fold_theta = 1;    // fold the theta GEMM's split-K partials into the noise GEMV's output (dne_set_option("fold_theta", v))
 int g_dne_fuse_head = 1;     // combine + output head in one kernel (dne_set_option("fuse_head", v))
@@ -84,6 +85,7 @@ extern "C" int dne_set_option(const char* name, int value) {
     if (strcmp(name, "gemv_stages") == 0 && value >= 2 && value <= 8) { extern int g_dne_gemv_stages; g_dne_gemv_stages = value; return DNE_OK; }
     if (strcmp(name, "gemv_prefetch") == 0 && value >= 0 && value <= 256) { extern int g_dne_gemv_prefetch; g_dne_gemv_prefetch = value; return DNE_OK; }
     if (strcmp(name, "fold_theta") == 0 && value >= 0 && value <= 1) { g_dne_fold_theta = value; return DNE_OK; }
+    if (strcmp(name, "chain_ticks") == 0 && value >= 0 && value <= 1) { g_dne_chain_ticks = value; return DNE_OK; }
     if (strcmp(name, "pdl") == 0 && value >= 0 && value <= 1) { g_dne_pdl = value; return DNE_OK; }
     if (strcmp(name, "gemv_balance") == 0 && value >= 0 && value <= 1) { extern int g_dne_gemv_balance; g_dne_gemv_balance = value; return DNE_OK; }
     if (strcmp(name, "gemv_grid") == 0 && value >= 0) { extern int g_dne_gemv_grid; g_dne_gemv_grid = value; return DNE_OK; }

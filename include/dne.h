@@ -102,6 +102,9 @@ long long   dne_launch_count(int reset);
  *   "fuse_head" = 1 (default): combine + output head + argmax in one kernel.
  *   "fold_theta" = 1 (default): the theta GEMM's split-K partials are folded into the noise GEMV's output.
  *   "pdl" = 1 (default): the tick's kernels are chained by programmatic dependent launch (griddepcontrol).
+ *   "chain_ticks" = 0 (default): 1 = the tick's first convolution is a dependent launch too; only valid when the stream's
+ *               previous kernel is the previous tick's last kernel (nothing that writes theta / the noise table / the slot table).
+ *   "gemv_balance" = 1 (default): the GEMV grid size is chosen to balance the round-robin deal of work items.
  *   "gemv_bulk" = 1 (default): noise GEMV through the cp.async.bulk shared-memory ring; 0 = plain-LDG kernel.
  *   "gemv_ctas_per_sm" = 1|2 (default 2), "gemv_stages" = 2..8 (default 6), "gemv_grid" (default 0 = no cap),
  *   "gemv_chunk_kb" (work-item size), "gemv_prefetch" = 0..256 (default 0; L2 prefetch distance, measured slower). */
