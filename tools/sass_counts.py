@@ -10,7 +10,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "deep-neuroevolution_b200", "dne", "libdne.so")
 txt = subprocess.run(["cuobjdump", "-sass", LIB], capture_output=True, text=True).stdout
 pat = {"UTCHMMA": r"\bUTCHMMA\b", "UTCBAR": r"\bUTCBAR\b", "LDTM": r"\bLDTM\b", "UBLKCP": r"\bUBLKCP\b", "UBLKPF": r"\bUBLKPF\b",
-       "UTMALDG": r"\bUTMALDG\b", "SYNCS": r"\bSYNCS\b", "HMMA": r"\bHMMA\b", "F2FP": r"\bF2FP\b"}
+       "UTMALDG": r"\bUTMALDG\b", "SYNCS": r"\bSYNCS\b", "HMMA": r"\bHMMA\b", "F2FP": r"\bF2FP\b",
+       "ACQBULK": r"\bACQBULK\b", "PREEXIT": r"\bPREEXIT\b"}
 rows = []
 for p in re.split(r"\n\s*Function : ", txt)[1:]:
     name = p.split("\n", 1)[0].strip()
@@ -21,7 +22,8 @@ for p in re.split(r"\n\s*Function : ", txt)[1:]:
     rows.append((name, len(re.findall(r"/\*[0-9a-f]{4}\*/", p)), {k: len(re.findall(v, p)) for k, v in pat.items()}))
 out = ["# r02 SASS evidence (`cuobjdump -sass deep-neuroevolution_b200/dne/libdne.so`, sm_100a)", "",
        "Per-kernel counts of the Blackwell-specific mnemonics (B200_PROFILING.md: `tcgen05.mma` -> `UTC*MMA`, `tcgen05.commit` ->",
-       "`UTCBAR`, `tcgen05.ld` -> `LDTM`, `cp.async.bulk` -> `UBLKCP`, mbarrier -> `SYNCS`, packed fp16 convert -> `F2FP`).",
+       "`UTCBAR`, `tcgen05.ld` -> `LDTM`, `cp.async.bulk` -> `UBLKCP`, mbarrier -> `SYNCS`, packed fp16 convert -> `F2FP`,",
+       "`griddepcontrol.wait` -> `ACQBULK`, `griddepcontrol.launch_dependents` -> `PREEXIT`: programmatic dependent launch).",
        "Regenerate: `python tools/sass_counts.py`.", "", "| kernel | SASS instr | " + " | ".join(pat) + " |",
        "|---|---|" + "---|" * len(pat)]
 tot = collections.Counter()
@@ -40,7 +42,7 @@ out += ["",
         "(measured slower, off by default).",
         "* `gemv_bulk_kernel<G>`: the HBM-bound noise GEMV, cp.async.bulk ring (the dominant kernel of the tick).",
         "* `conv_tc_kernel` / `theta_gemm_tc_kernel`: the r01 thread-staged tcgen05 kernels (kind::tf32), kept for A/B "
-        "(`dne_set_option(\"conv_tc\", 1)`) and used by the virtual-batch-norm reference pass.",
+        "(`dne_set_option(\"conv_tc\", 1)`).  `member_gemm_tc_kernel`: the fc of the virtual-batch-norm reference pass.",
         "* `UTMALDG` = 0 by design: every TMA transfer on this path is one contiguous run (images, weight rows and GEMM operands are "
         "laid out for that), so the descriptor-less bulk form is what the data layout calls for.  `HMMA` = 0: no legacy "
         "mma.sync / wmma anywhere."]
