@@ -71,7 +71,7 @@ class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap,enforced.power.limit")
+         "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index=0):
         self.rows, self.proc, self.gpu = [], None, gpu_index
@@ -104,7 +104,13 @@ class ClockSampler:
             except ValueError:
                 return None
         pw = [num(r[3]) for r in self.rows if len(r) >= 8 and num(r[3]) is not None]
-        lim = [num(r[8]) for r in self.rows if len(r) >= 9 and num(r[8]) is not None]
+        lim = []
+        try:                                                      # one separate query: an unknown field must not cost the clock samples
+            out = subprocess.run(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=enforced.power.limit",
+                                  "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=10).stdout
+            lim = [v for v in (num(x.strip()) for x in out.splitlines()) if v is not None]
+        except Exception:
+            pass
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
                 "reasons": reasons, "samples": len(sm), "power_w": float(np.median(pw)) if pw else None,
                 "power_limit_w": max(lim) if lim else None}
