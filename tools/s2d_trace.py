@@ -3,6 +3,7 @@ dne/libdne_trace.so; run with DNE_LIB=.../libdne_trace.so).  Prints clock64 delt
 import os, sys, ctypes as C
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "deep-neuroevolution_b200")]
+# build it first: make -C deep-neuroevolution_b200/csrc trace
 os.environ.setdefault("DNE_LIB", os.path.join(ROOT, "deep-neuroevolution_b200", "dne", "libdne_trace.so"))
 import numpy as np, torch
 from dne import _ffi as F, nets
