@@ -7,7 +7,8 @@ uint8 84x84x4 observations, fixed episode length T (default 1000 env steps), pop
 One "step" = one GENERATION: rollouts of this rank's shard of the population for T ticks each, then the update
 (all_gather returns -> centred ranks -> ES gradient over the local noise indices -> all_reduce(g) -> Adam).
 
-  value   device-resident: observations / rewards already in HBM when the timed region starts.
+  value   device-resident: observations / rewards already in HBM when the timed region starts; ticks launched kernel by
+          kernel, kernels and consecutive ticks chained by programmatic dependent launch (DNE_BENCH_GRAPH=1: CUDA graphs).
   e2e     the same generation through the public API es_distributed.es.run_master with a HOST environment: every
           tick copies that tick's observations host->device from pinned memory and the actions device->host.
   --impl reference   the reference worker/master loop restated on the CPU (oracle/cpu_worker.py) on all host cores.

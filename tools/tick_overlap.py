@@ -1,7 +1,8 @@
 """Dev tool (GPU box): steady-state time of one ROUND (every slot of the GPU ticks once) when the slot table is split into
 NT tables on NT streams (CUDA-graph replays, no cross-stream ordering), against the single-table tick.  The HBM-bound
-noise GEMV of one table can then overlap the tensor-core kernels of another when the GEMV leaves whole SMs free
-(DNE_OPTS=gemv_ctas_per_sm=1,gemv_stages=8,gemv_grid=G).  Not a bench."""
+noise GEMV of one table could overlap the tensor-core kernels of another if the GEMV left whole SMs free
+(OPT_SETS="a=1,b=2;a=1,b=3" loops over option sets, e.g. gemv_ctas_per_sm=1,gemv_stages=8,gemv_grid=G; SLOTS_LIST, TABLES).
+Result: it does not pay -- the GEMV needs 2 CTAs/SM on all SMs.  Not a bench."""
 import os, sys, json
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "deep-neuroevolution_b200")]
