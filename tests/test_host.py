@@ -339,3 +339,27 @@ def test_make_env_real_ids_need_opt_in(monkeypatch):
     with pytest.raises(KeyError):
         envs.make_env("NoSuchEnv-v0", 2)
 
+
+
+def test_bench_clock_sampler_and_reference_arm_contract(tmp_path):
+    """bench.py pieces that run without a GPU: the clock sampler degrades to a labelled record when nvidia-smi is missing or
+    prints nothing useful, and `--impl reference` prints one JSON line with the driver's keys (a tiny sample here)."""
+    import importlib.util
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(root, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    s = bench.ClockSampler(0)
+    s.start()
+    rec = s.stop()
+    assert {"sm_mhz", "sm_max_mhz", "reasons"} <= set(rec)
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                          "--pop", "8", "--episode-len", "20", "--cpu-sample-steps", "4"], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "env-steps/s" and line["higher_is_better"] is True
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["cpu_baseline"]["kind"] in ("port", "reference")
+    assert line["value"] > 0 and line["config"]["workload"].startswith("frostbite_es")
