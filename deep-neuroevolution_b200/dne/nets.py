@@ -139,7 +139,7 @@ def make_net(name: str, num_actions: int = 18, ob_dim: int = 376, hidden: Sequen
         return _finish(NetSpec(name, layers, F.OB_ATARI_U8, 84 * 84 * 4))
     if name == "ModelVirtualBN":                 # gpu_implementation/neuroevolution/models/batchnorm.py:50-123
         layers = [_conv(4, 16, 8, 4, 84, bn=F.BN_GPU), _conv(16, 32, 4, 2, 21, bn=F.BN_GPU),
-                  _dense(11 * 11 * 32, 256, bn=F.BN_GPU), _dense(256, A, act=F.ACT_NONE, std=ac_init_std)]
+                  _dense(11 * 11 * 32, 256, bn=F.BN_GPU), _dense(256, A, act=F.ACT_NONE, std=1.0)]   # 'out': default std (batchnorm.py:106)
         return _finish(NetSpec(name, layers, F.OB_ATARI_U8, 84 * 84 * 4))
     if name == "MujocoPolicy":
         act = {"tanh": F.ACT_TANH, "relu": F.ACT_RELU}[nonlin]

@@ -289,8 +289,10 @@ def make_net(name: str, num_actions: int = 18, ob_dim: int = 376, hidden=(256, 2
         # gpu_implementation/neuroevolution/models/batchnorm.py:50-123: conv / dense WITHOUT bias, then
         # (x - mean) * 1/sqrt(var + 1e-3) + b with a per-channel bias b created inside the BatchNorm scope (no gamma):
         # creation order w, b per layer -- the same flat layout as Model, but 'b' acts AFTER the normalisation
+        # the output layer is created with the DEFAULT std = 1.0 (batchnorm.py:106, unlike Model / LargeModel's 0.1): found by
+        # executing the reference class (tests/golden/make_golden_models.py)
         layers = [conv(4, 16, 8, 4, 84, bn="vbn_gpu"), conv(16, 32, 4, 2, 21, bn="vbn_gpu"),
-                  dense(11 * 11 * 32, 256, bn="vbn_gpu"), dense(256, A, act="none", std=0.1)]
+                  dense(11 * 11 * 32, 256, bn="vbn_gpu"), dense(256, A, act="none", std=1.0)]
         return _finish(Net(name, layers, (84, 84, 4)))
     if name == "MujocoPolicy":
         dims = [ob_dim] + list(hidden)

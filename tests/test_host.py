@@ -357,7 +357,7 @@ def test_bench_clock_sampler_and_reference_arm_contract(tmp_path):
     rec = s.stop()
     assert {"sm_mhz", "sm_max_mhz", "reasons"} <= set(rec)
     out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
-                          "--pop", "8", "--episode-len", "20", "--cpu-sample-steps", "4"], capture_output=True, text=True, timeout=600)
+                          "--pop", "8", "--episode-len", "20", "--cpu-sample-steps", "2", "--noise-count", "6000000"], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stderr[-2000:]
     line = json.loads(out.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["unit"] == "env-steps/s" and line["higher_is_better"] is True

@@ -279,3 +279,53 @@ def test_warp_frame_gpu_formula_properties():
     assert out.min() >= g.min() - 1e-6 and out.max() <= g.max() + 1e-6
     const = np.full((2, 210, 160), 6, dtype=np.uint8)
     np.testing.assert_array_equal(O.warp_frame_gpu(const, pal), np.full((84, 84), pal[6], dtype=np.float32))
+
+
+# --------------------------------------------------------------------------------------------------
+# Pinned to the reference's OWN model classes, executed under a shape-only TensorFlow stand-in
+# (tests/golden/make_golden_models.py -> ref_models.npz): flat layout (8a-3), initialisation scale and seed-chain
+# genome materialisation (8a-11) of gpu_implementation/neuroevolution/models/{base,dqn,batchnorm}.py.
+# --------------------------------------------------------------------------------------------------
+import os  # noqa: E402
+
+_REF_MODELS = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_models.npz")
+
+
+@pytest.mark.parametrize("name", ["Model", "LargeModel", "ModelVirtualBN"])
+def test_layout_and_init_scale_match_reference_models(name):
+    g = np.load(_REF_MODELS)
+    net = O.make_net(name)
+    ref_names = [str(s) for s in g[f"{name}.names"]]
+    ref_shapes = [tuple(int(d) for d in str(s).split(",")) for s in g[f"{name}.shapes"]]
+    assert net.num_params == int(g[f"{name}.num_params"])
+    got = net.variables()
+    assert len(got) == len(ref_names)
+    off = 0
+    for v, rn, rsh in zip(got, ref_names, ref_shapes):
+        assert rn.split("/")[-1] == ("w" if v.kind == "w" else "b"), (rn, v)            # creation order: w then b per layer
+        assert int(np.prod(rsh)) == v.size and tuple(d for d in rsh if d != 1) == tuple(d for d in v.shape if d != 1), (rn, rsh, v.shape)
+        assert v.offset == off
+        off += v.size
+    # per-variable initialisation scale, rounded to float32 as numpy 1.x does when it multiplies the float32 ones vector
+    scale = O.ga_scale_by(net)
+    for v, s in zip(got, g[f"{name}.var_scale_by"]):
+        assert np.all(scale[v.offset:v.offset + v.size] == np.float32(s)), (v.name, float(s))
+    assert abs(float(scale.astype(np.float64).sum()) - float(g[f"{name}.scale_by_sum"])) <= 1e-6 * float(g[f"{name}.scale_by_sum"])
+
+
+@pytest.mark.parametrize("name", ["Model", "LargeModel", "ModelVirtualBN"])
+def test_genome_materialisation_matches_reference_models(name):
+    """base.py:127-156 executed by the reference itself (float64 under numpy >= 2, see the generator's note) against the
+    float32 oracle: every sampled coordinate within float32 rounding of the 4-term chain."""
+    g = np.load(_REF_MODELS)
+    net = O.make_net(name)
+    noise = O.noise_table(24_000_000)
+    idx, power = g[f"{name}.seed_idx"], g[f"{name}.seed_power"]
+    seeds = (int(idx[0]),) + tuple((int(i), float(p)) for i, p in zip(idx[1:], power[1:]))
+    theta = O.ga_materialize_gpu(net, noise, seeds)
+    assert theta.dtype == np.float32
+    ref = g[f"{name}.theta_samples"]
+    np.testing.assert_allclose(theta[::997].astype(np.float64), ref, rtol=3e-7, atol=1e-9)
+    t64 = theta.astype(np.float64)
+    assert abs(t64.sum() - float(g[f"{name}.theta_sum"])) <= 1e-4
+    assert abs(np.square(t64).sum() - float(g[f"{name}.theta_sumsq"])) <= 1e-6 * float(g[f"{name}.theta_sumsq"])
