@@ -363,3 +363,17 @@ def test_bench_clock_sampler_and_reference_arm_contract(tmp_path):
     assert line["impl"] == "reference" and line["unit"] == "env-steps/s" and line["higher_is_better"] is True
     assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["cpu_baseline"]["kind"] in ("port", "reference")
     assert line["value"] > 0 and line["config"]["workload"].startswith("frostbite_es")
+
+
+def test_normc_initialiser_matches_reference_bit_exactly():
+    """tf_util.normc_initializer (tf_util.py:108-119) executed by tests/golden/make_golden_policies.py on the global numpy stream
+    vs the package's initialiser on a RandomState with the same seed."""
+    import hashlib
+    from es_distributed.policies import _normc
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_policies.npz"))
+    for i in range(4):
+        shape, std = tuple(int(d) for d in g[f"normc.{i}.shape"]), float(g[f"normc.{i}.std"])
+        arr = _normc(np.random.RandomState(1000 + i), shape, std)
+        assert arr.dtype == np.float32 and arr.shape == shape
+        np.testing.assert_array_equal(arr.reshape(-1)[:16], g[f"normc.{i}.head"])
+        assert hashlib.sha1(np.ascontiguousarray(arr).tobytes()).hexdigest() == str(g[f"normc.{i}.sha1"])

@@ -329,3 +329,45 @@ def test_genome_materialisation_matches_reference_models(name):
     t64 = theta.astype(np.float64)
     assert abs(t64.sum() - float(g[f"{name}.theta_sum"])) <= 1e-4
     assert abs(np.square(t64).sum() - float(g[f"{name}.theta_sumsq"])) <= 1e-6 * float(g[f"{name}.theta_sumsq"])
+
+
+# --------------------------------------------------------------------------------------------------
+# Pinned to the reference's CPU-path builders (es_distributed/policies.py `_make_net` + tf_util layer functions) executed
+# under the shape-only TensorFlow stand-in of tests/golden/make_golden_policies.py -> ref_policies.npz
+# --------------------------------------------------------------------------------------------------
+_REF_POLICIES = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_policies.npz")
+
+
+@pytest.mark.parametrize("key,name,kw", [
+    ("GAAtariPolicy", "GAAtariPolicy", {}),
+    ("MujocoPolicy.continuous", "MujocoPolicy", dict(ob_dim=376, hidden=(256, 256), ac_dim=17)),
+    ("MujocoPolicy.uniform10", "MujocoPolicy", dict(ob_dim=376, hidden=(256, 256), ac_dim=170)),
+])
+def test_flat_layout_matches_reference_policy_builders(key, name, kw):
+    """tf_util.GetFlat / SetFromFlat (tf_util.py:224-246) concatenate the trainable variables in creation order."""
+    g = np.load(_REF_POLICIES)
+    net = O.make_net(name, **kw)
+    names = [str(s) for s in g[key + ".names"]]
+    shapes = [tuple(int(d) for d in str(s).split(",")) for s in g[key + ".shapes"]]
+    assert net.num_params == int(g[key + ".num_params"])
+    got = net.variables()
+    assert len(got) == len(names)
+    off = 0
+    for v, rn, rsh in zip(got, names, shapes):
+        assert rn.split("/")[-1] == ("w" if v.kind == "w" else "b"), (rn, v)
+        assert int(np.prod(rsh)) == v.size and tuple(d for d in rsh if d != 1) == tuple(d for d in v.shape if d != 1), (rn, rsh, v.shape)
+        assert v.offset == off
+        off += v.size
+
+
+def test_reinitialize_matches_reference_closures_bit_exactly():
+    """Policy.reinitialize (policies.py:42-44): the numpy closure of tf_util._normalize run by the generator on a seeded flat
+    vector, variable by variable, against oracle.ga_reinitialize -- every bit."""
+    import hashlib
+    g = np.load(_REF_POLICIES)
+    net = O.make_net("GAAtariPolicy")
+    flat = np.random.RandomState(int(g["GAAtariPolicy.reinit_in_seed"])).randn(net.num_params).astype(np.float32)
+    out = O.ga_reinitialize(net, flat)
+    assert out.dtype == np.float32
+    np.testing.assert_array_equal(out[::499], g["GAAtariPolicy.reinit_samples"])
+    assert hashlib.sha1(out.tobytes()).hexdigest() == str(g["GAAtariPolicy.reinit_sha1"])
