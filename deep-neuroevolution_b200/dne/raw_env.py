@@ -2,9 +2,12 @@
 observation pipeline of the reference on the device.
 
 Reference pipeline per agent step (es_distributed/atari_wrappers.py ``wrap_deepmind``, :204-222):
-  NoopResetEnv (:8-27, up to 30 no-ops)  ->  MaxAndSkipEnv (:86-107: repeat the action 4 times, sum the rewards, observation =
-  per-pixel max of the last two raw frames)  ->  WarpFrame (:129-142: gray + PIL BILINEAR 210x160 -> 84x84 uint8)  ->
+  NoopResetEnv (:8-31, up to 30 no-ops)  ->  MaxAndSkipEnv (:86-107: repeat the action 4 times, sum the rewards, observation =
+  per-pixel max of the last two raw frames)  ->  FireResetEnv (:33-48, games whose action 1 is FIRE -- Frostbite is one: on
+  reset one agent step of FIRE and one of action 2)  ->  WarpFrame (:129-142: gray + PIL BILINEAR 210x160 -> 84x84 uint8)  ->
   FrameStack(4) (:167-180)  ->  ScaledFloatFrame (:182-186, /255: folded into the conv1 epilogue on the device).
+The host-side logic (reset / skip / done handling) is pinned to the reference's own wrapper classes, executed on these
+emulators under an old-gym stand-in (tests/golden/make_golden_wrappers.py, tests/test_host.py).
 On the reference GPU path the emulators run on TF's CPU thread pool (gym_tensorflow/tf_env.cpp:231-316,
 atari/tf_atari.cpp:24-128) and max / gray / resize / stack are TF ops (tf_atari.py:88-92, wrappers/stack_frames.py:33-43).
 
@@ -19,6 +22,7 @@ ALE itself is not vendored by the reference and is absent from this image: ``Syn
 from (seed, t, action)) stands in for tests; ``ALEEmulator`` adapts ``ale_py`` when it is importable."""
 from __future__ import annotations
 
+import threading
 from concurrent.futures import ThreadPoolExecutor
 from typing import Callable, List, Optional
 
@@ -29,11 +33,16 @@ from . import _ffi as F
 from .envs import BatchEnv, Box, Discrete
 
 RAW_H, RAW_W = 210, 160
+# ALE's 18 actions in index order (gym's ACTION_MEANING table): what FireResetEnv / NoopResetEnv look at
+ALE_ACTION_MEANINGS = ["NOOP", "FIRE", "UP", "RIGHT", "LEFT", "DOWN", "UPRIGHT", "UPLEFT", "DOWNRIGHT", "DOWNLEFT", "UPFIRE", "RIGHTFIRE",
+                       "LEFTFIRE", "DOWNFIRE", "UPRIGHTFIRE", "UPLEFTFIRE", "DOWNRIGHTFIRE", "DOWNLEFTFIRE"]
 
 
 class Emulator:
-    """One game instance.  ``reset() -> frame``, ``act(a) -> (reward, game_over, frame)`` with frame uint8 [210,160,3]."""
+    """One game instance.  ``reset() -> frame``, ``act(a) -> (reward, game_over, frame)`` with frame uint8 [210,160,3].
+    ``action_meanings``: optional list of names (gym's get_action_meanings); [1] == 'FIRE' switches the fire-reset on."""
     num_actions = 18
+    action_meanings = None
 
     def reset(self) -> np.ndarray:
         raise NotImplementedError
@@ -76,6 +85,7 @@ class ALEEmulator(Emulator):          # pragma: no cover - needs ale_py + a ROM,
         self.ale.loadROM(rom_path)
         self.actions = self.ale.getMinimalActionSet()
         self.num_actions = len(self.actions)
+        self.action_meanings = [ALE_ACTION_MEANINGS[int(a)] for a in self.actions]
 
     def reset(self):
         self.ale.reset_game()
@@ -88,7 +98,10 @@ class ALEEmulator(Emulator):          # pragma: no cover - needs ale_py + a ROM,
 
 class RawFrameAtariEnv(BatchEnv):
     def __init__(self, emulators: List[Emulator], frame_skip: int = 4, noop_max: int = 30, max_episode_steps: Optional[int] = None,
-                 seed: int = 0, threads: Optional[int] = None, device=None):
+                 seed: int = 0, threads: Optional[int] = None, device=None, fire_reset: Optional[bool] = None,
+                 noops: Optional[int] = None):
+        """``fire_reset``: FireResetEnv of the reference (None = when the emulators' action 1 is 'FIRE', atari_wrappers.py:217);
+        ``noops``: fixed number of reset no-ops (wrap_deepmind's ``noops`` override, :211-212) instead of a draw in [1, noop_max]."""
         self.emus = list(emulators)
         self.n_slots = len(self.emus)
         self.observation_space = Box(0, 255, (84, 84, 4), dtype=np.uint8)
@@ -96,24 +109,41 @@ class RawFrameAtariEnv(BatchEnv):
         self.skip, self.noop_max = int(frame_skip), int(noop_max)
         self.max_episode_steps = max_episode_steps
         self.rs = np.random.RandomState(seed)
-        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        meanings = getattr(self.emus[0], "action_meanings", None)
+        self.fire_reset = bool(meanings and len(meanings) >= 3 and meanings[1] == "FIRE") if fire_reset is None else bool(fire_reset)
+        self.noops = noops
+        if device is None:                                               # (host-only use -- the CPU tests -- needs no CUDA device)
+            device = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else torch.device("cpu")
+        self.device = torch.device(device)
         pin = torch.cuda.is_available()
         raw = torch.zeros(self.n_slots, 2, RAW_H, RAW_W, 3, dtype=torch.uint8)
         self.raw = raw.pin_memory() if pin else raw                      # last two raw frames of the current agent step
         self._raw_np = self.raw.numpy()
         self.fresh = np.zeros(self.n_slots, dtype=np.uint8)              # episode just (re)started: stack = first frame x 4
         self.pool = ThreadPoolExecutor(max_workers=threads or min(32, self.n_slots))
+        self._rs_lock = threading.Lock()
         self._dev = {}                                                   # (lo, hi) -> device buffers
         self.ram = np.zeros((self.n_slots, 128), dtype=np.uint8)
 
     # -- host side: emulator stepping on the thread pool -----------------------------------------------------------
-    def _reset_one(self, s, noops):
+    def _noop_reset(self, s, noops):
         f = self.emus[s].reset()
-        for _ in range(noops):                                           # atari_wrappers.py:17-25 (action 0 = NOOP)
+        for _ in range(noops):                                           # atari_wrappers.py:25-30 (action 0 = NOOP, raw env steps)
             _, over, f = self.emus[s].act(0)
             if over:
                 f = self.emus[s].reset()
         self._raw_np[s, 0] = self._raw_np[s, 1] = f                      # MaxAndSkipEnv._reset (:109-114): buffer = [first frame]
+
+    def _reset_one(self, s, noops):
+        """NoopResetEnv._reset + MaxAndSkipEnv._reset (+ FireResetEnv._reset, atari_wrappers.py:40-48)."""
+        self._noop_reset(s, noops)
+        if self.fire_reset:
+            for a in (1, 2):                                             # one agent step of FIRE, one of action 2
+                _, over = self._step_one(s, a)
+                if over:                                                 # "if done: self.env.reset()": the inner stack again, with
+                    with self._rs_lock:                                  # a fresh no-op draw.  (After the action-2 step the
+                        k = int(self._draw_noops(1)[0])                  # reference still returns that step's frame; here the
+                    self._noop_reset(s, k)                               # fresh game's first frame -- unreachable with real games.)
 
     def _step_one(self, s, a):
         total, over = 0.0, False
@@ -127,10 +157,14 @@ class RawFrameAtariEnv(BatchEnv):
         self._raw_np[s, 0], self._raw_np[s, 1] = prev, cur
         return total, over
 
+    def _draw_noops(self, n):
+        if self.noops is not None:
+            return np.full(n, int(self.noops), dtype=np.int64)
+        return self.rs.randint(1, self.noop_max + 1, size=n) if self.noop_max > 0 else np.zeros(n, dtype=np.int64)
+
     def reset(self, slots):
         slots = np.asarray(slots, dtype=np.int64)
-        noops = self.rs.randint(1, self.noop_max + 1, size=len(slots)) if self.noop_max > 0 else np.zeros(len(slots), int)
-        list(self.pool.map(self._reset_one, slots.tolist(), noops.tolist()))
+        list(self.pool.map(self._reset_one, slots.tolist(), self._draw_noops(len(slots)).tolist()))
         self.fresh[slots] = 1
 
     def step(self, slots, actions):

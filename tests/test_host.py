@@ -377,3 +377,43 @@ def test_normc_initialiser_matches_reference_bit_exactly():
         assert arr.dtype == np.float32 and arr.shape == shape
         np.testing.assert_array_equal(arr.reshape(-1)[:16], g[f"normc.{i}.head"])
         assert hashlib.sha1(np.ascontiguousarray(arr).tobytes()).hexdigest() == str(g[f"normc.{i}.sha1"])
+
+
+def test_raw_env_host_logic_matches_reference_wrappers():
+    """dne/raw_env.py RawFrameAtariEnv (no-op reset, frame skip with break on game over, fire reset, last-two-frames buffer, episode
+    restart) + the oracle's warp / frame stack, against the reference's own wrap_deepmind stack executed on the same emulator
+    (tests/golden/make_golden_wrappers.py): raw step counter, rewards, dones and the sha1 of every uint8 frame stack."""
+    import hashlib
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import wrappers_common as WC
+    from dne.raw_env import RawFrameAtariEnv
+    from oracle import oracle as O
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_wrappers.npz"))
+    emu = WC.RedOnlyEmulator(WC.EMU_SEED, frames=WC.EMU_FRAMES)
+    env = RawFrameAtariEnv([emu], noop_max=30, seed=WC.ENV_SEED, device="cpu")
+    assert env.fire_reset                                        # action 1 is FIRE
+    stack = np.zeros((1, 84, 84, 4), dtype=np.uint8)
+    ev = [0]
+
+    def check(kind, r, d):
+        nonlocal stack
+        i = ev[0]
+        frame = O.warp_frame_cpu(np.maximum(env._raw_np[0, 0], env._raw_np[0, 1]))[None]       # max of the last two raw frames, then warp
+        stack = O.max_and_stack(frame, frame, stack, env.fresh[:1].astype(bool), mode="cpu")
+        env.fresh[:] = 0
+        assert int(g["kind"][i]) == kind and int(g["emu_t"][i]) == emu.t, (i, kind, emu.t, int(g["emu_t"][i]))
+        assert float(g["reward"][i]) == float(r) and bool(g["done"][i]) == bool(d), i
+        if i == 0:
+            np.testing.assert_array_equal(stack[0], g["first_stack"])
+        assert hashlib.sha1(np.ascontiguousarray(stack[0]).tobytes()).hexdigest() == str(g["sha1"][i]), i
+        ev[0] += 1
+
+    env.reset([0])
+    check(0, 0.0, False)
+    for a in WC.ACTIONS:
+        rew, done = env.step([0], [a])
+        check(1, rew[0], done[0])
+        if done[0]:
+            env.reset([0])
+            check(0, 0.0, False)
+    assert ev[0] == len(g["kind"])
