@@ -417,3 +417,19 @@ def test_raw_env_host_logic_matches_reference_wrappers():
             env.reset([0])
             check(0, 0.0, False)
     assert ev[0] == len(g["kind"])
+
+
+def test_vine_export_bytes_match_reference_functions(tmp_path):
+    """The exact bytes es_modified.py `master_extract_cloud` / `master_extract_parent` wrote for the seeded input of
+    tests/golden/make_golden_vine.py (the reference functions themselves, executed in the build container)."""
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import make_golden_vine as G
+    from es_distributed.es import vine_export_cloud, vine_export_parent
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_vine.npz"))
+    _, cloud, evals, rets = G.inputs()
+    path = vine_export_cloud(str(tmp_path), 7, cloud)
+    vine_export_parent(str(tmp_path), 7, [e[:4] for e in evals], rets, evals[0][4])
+    assert open(os.path.join(path, "snapshot_offspring_0007.dat"), "rb").read() == g["offspring"].tobytes()
+    assert open(os.path.join(path, "snapshot_parent_0007.dat"), "rb").read() == g["parent"].tobytes()
+    assert path.endswith(os.path.join("snapshots", "snapshot_gen_0007"))
+    assert {"snapshot_offspring_0007.dat", "snapshot_parent_0007.dat"} <= {str(f) for f in g["files"]}
