@@ -167,7 +167,9 @@ def set_quiet(q=True):
 
 
 def log(*args):
-    msg = " ".join(str(a) for a in args)
+    # tabular_logger.py:171-179: the strings are written back to back (no separator), then a newline; non-string arguments
+    # (an extension: the reference's f.write would raise) are joined with spaces
+    msg = "".join(args) if all(isinstance(a, str) for a in args) else " ".join(str(a) for a in args)
     if not _state["quiet"]:
         sys.stdout.write(msg + "\n")
         sys.stdout.flush()
@@ -184,7 +186,9 @@ def dump_tabular():
     row = _state["row"]
     if not row:
         return
-    items = [(k, ("%-8.3g" % v) if hasattr(v, "__float__") else str(v)) for k, v in row.items()]
+    def trunc(t):                                                       # tabular_logger.py:180-184
+        return t[:30] + "..." if len(t) > 33 else t
+    items = [(trunc(k), trunc(("%-8.3g" % v) if hasattr(v, "__float__") else str(v))) for k, v in row.items()]
     kw = max(len(k) for k, _ in items)
     vw = max(len(v) for _, v in items)
     dashes = "-" * (kw + vw + 7)

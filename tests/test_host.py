@@ -433,3 +433,20 @@ def test_vine_export_bytes_match_reference_functions(tmp_path):
     assert open(os.path.join(path, "snapshot_parent_0007.dat"), "rb").read() == g["parent"].tobytes()
     assert path.endswith(os.path.join("snapshots", "snapshot_gen_0007"))
     assert {"snapshot_offspring_0007.dat", "snapshot_parent_0007.dat"} <= {str(f) for f in g["files"]}
+
+
+def test_log_txt_bytes_match_reference_logger(tmp_path):
+    """log.txt of the package's tabular_logger vs the bytes the reference's own tabular_logger.py wrote for the same scripted calls
+    (tests/golden/make_golden_logger.py): table layout, %-8.3g values, key truncation, back-to-back `log` strings."""
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import make_golden_logger as G
+    from es_distributed import tabular_logger as L
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_logger.npz"))
+    L.set_quiet(True)
+    try:
+        L.start(str(tmp_path))
+        G.script(L)
+    finally:
+        L.stop()
+        L.set_quiet(False)
+    assert open(os.path.join(str(tmp_path), "log.txt"), "rb").read() == g["log_txt"].tobytes()
