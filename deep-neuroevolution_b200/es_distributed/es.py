@@ -180,6 +180,34 @@ class GenerationStats(dict):
     pass
 
 
+# The keys the reference's masters log every iteration, in their order (es.py:313-339, ga.py:171-196, nses.py:256-284,
+# rs.py; tests/golden/ref_log_keys.json is that list extracted from the reference sources).
+REF_ROW_KEYS = {
+    "ga": ["EpRewMax", "EpRewMean", "EpRewStd", "EpLenMean", "EvalEpRewMean", "EvalEpRewMedian", "EvalEpRewStd", "EvalEpLenMean",
+           "EvalPopRank", "EvalEpCount", "Norm", "EpisodesThisIter", "EpisodesSoFar", "TimestepsThisIter", "TimestepsSoFar",
+           "UniqueWorkers", "UniqueWorkersFrac", "ResultsSkippedFrac", "ObCount", "TimeElapsedThisIter", "TimeElapsed"],
+    "nses": ["ParentId", "EpRewMean", "EpRewStd", "EpLenMean", "EvalEpRewMean", "EvalEpRewStd", "EvalEpLenMean", "EvalPopRank",
+             "EvalEpCount", "Norm", "GradNorm", "UpdateRatio", "EpisodesThisIter", "EpisodesSoFar", "TimestepsThisIter",
+             "TimestepsSoFar", "UniqueWorkers", "UniqueWorkersFrac", "ResultsSkippedFrac", "ObCount", "TimeElapsedThisIter",
+             "TimeElapsed"],
+}
+REF_ROW_KEYS["rs"] = list(REF_ROW_KEYS["ga"])
+_ROW_DEFAULTS = dict(EvalEpRewMean=float("nan"), EvalEpRewMedian=float("nan"), EvalEpRewStd=float("nan"),
+                     EvalEpLenMean=float("nan"), EvalPopRank=float("nan"), EvalEpCount=0, UniqueWorkersFrac=1.0,
+                     ResultsSkippedFrac=0.0, ObCount=0)
+
+
+def reference_row(kind, stats, world=1):
+    """``stats`` as the row the reference's master of this algorithm logs: every reference key, in the reference's order, then
+    this engine's extra keys.  Keys without a counterpart here get the reference's own "nothing happened" value (no evaluation
+    episodes this iteration: NaN statistics and EvalEpCount 0; no stale results; one 'worker' per rank)."""
+    d = dict(_ROW_DEFAULTS, UniqueWorkers=world)
+    d.update(stats)
+    out = {k: d[k] for k in REF_ROW_KEYS[kind]}
+    out.update({k: v for k, v in stats.items() if k not in out})
+    return out
+
+
 def vine_export_cloud(root, iteration, bc_vectors):
     """es_modified.py:179-199 ``master_extract_cloud``: one row per offspring episode in
     ``<root>/snapshots/snapshot_gen_{it:04}/snapshot_offspring_{it:04}.dat`` = final BC row, fitness, length, noise index,

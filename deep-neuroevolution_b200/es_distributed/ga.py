@@ -26,7 +26,7 @@ from dne import _ffi as F
 from dne import shard
 from dne.rollout import RolloutRunner, Unit
 from .es import (Config, Result, Task, RunningStat, SharedNoiseTable, default_context, default_noise,   # noqa: F401
-                 set_default_noise, setup as _es_setup, _cutoff)
+                 set_default_noise, setup as _es_setup, _cutoff, reference_row)
 
 logger = logging.getLogger(__name__)
 
@@ -220,6 +220,7 @@ def run_master(master_redis_cfg, log_dir, exp, *, max_iterations=None, n_slots=2
                      TimestepsThisIter=int(lengths_n2.sum()), TimestepsSoFar=int(timesteps_so_far),
                      UniqueWorkers=world, TimeElapsedThisIter=step_tend - step_tstart, TimeElapsed=step_tend - tstart)
         stats.update(deep_stats)
+        stats = reference_row("ga", stats, world)                                      # the reference's keys, in its order
         if rank == 0:
             tlogger.log('Elite: {} score: {}'.format(elite if deep else population[0], population_score[0]))
             for k, v in stats.items():

@@ -26,7 +26,7 @@ from dne import _ffi as F
 from dne import shard
 from dne.rollout import RolloutRunner, Unit
 from .es import (Config, Result, Task, RunningStat, SharedNoiseTable, default_context, default_noise,   # noqa: F401
-                 set_default_noise, setup as _es_setup, _cutoff, _process_returns, get_ref_batch)
+                 set_default_noise, setup as _es_setup, _cutoff, _process_returns, get_ref_batch, reference_row)
 
 logger = logging.getLogger(__name__)
 
@@ -217,8 +217,9 @@ def run_master(master_redis_cfg, log_dir, exp, *, max_iterations=None, n_slots=2
                      Norm=float(torch.square(optimizer.device_theta).sum()), GradNorm=float(torch.square(g).sum()),
                      UpdateRatio=float(update_ratio), EpisodesThisIter=int(lengths_n2.size),
                      EpisodesSoFar=int(episodes_so_far), TimestepsThisIter=int(lengths_n2.sum()),
-                     TimestepsSoFar=int(timesteps_so_far), ArchiveSize=len(archive),
+                     TimestepsSoFar=int(timesteps_so_far), ObCount=int(ob_count_this_batch), ArchiveSize=len(archive),
                      TimeElapsedThisIter=time.time() - step_tstart, TimeElapsed=time.time() - tstart)
+        stats = reference_row("nses", stats, world)                                    # the reference's keys, in its order
         if rank == 0:
             for kk, v in stats.items():
                 tlogger.record_tabular(kk, v)

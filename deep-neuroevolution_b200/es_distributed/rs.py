@@ -17,7 +17,7 @@ import torch
 
 from dne import shard
 from dne.rollout import RolloutRunner, Unit
-from .es import SharedNoiseTable, default_context, default_noise, set_default_noise, _cutoff   # noqa: F401
+from .es import SharedNoiseTable, default_context, default_noise, set_default_noise, _cutoff, reference_row   # noqa: F401
 from .ga import GenomeCache, setup
 
 logger = logging.getLogger(__name__)
@@ -99,6 +99,7 @@ def run_master(master_redis_cfg, log_dir, exp, *, max_iterations=None, n_slots=2
                      EpisodesThisIter=int(lengths_n2.size), EpisodesSoFar=int(episodes_so_far),
                      TimestepsThisIter=int(lengths_n2.sum()), TimestepsSoFar=int(timesteps_so_far),
                      UniqueWorkers=world, TimeElapsedThisIter=step_tend - step_tstart, TimeElapsed=step_tend - tstart)
+        stats = reference_row("rs", stats, world)                                      # the reference's keys, in its order
         if rank == 0:
             for k, v in stats.items():
                 tlogger.record_tabular(k, v)

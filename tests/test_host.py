@@ -450,3 +450,33 @@ def test_log_txt_bytes_match_reference_logger(tmp_path):
         L.stop()
         L.set_quiet(False)
     assert open(os.path.join(str(tmp_path), "log.txt"), "rb").read() == g["log_txt"].tobytes()
+
+
+def test_logged_rows_carry_the_reference_keys_in_reference_order():
+    """log.txt rows of the GA / NS-ES / RS / ES masters: every key the reference's master records, in its order
+    (tests/golden/ref_log_keys.json = the record_tabular keys extracted from the reference sources), then the engine's extras.
+    The masters only run on a GPU, so this checks (a) es.reference_row itself and (b) statically, that each master passes a value
+    for every reference key that has no default -- a missing one would be a KeyError at run time."""
+    import ast
+    import json
+    from es_distributed import es as ES
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    ref = json.load(open(os.path.join(root, "tests", "golden", "ref_log_keys.json")))
+    for kind in ("ga", "nses", "rs"):
+        assert ES.REF_ROW_KEYS[kind] == ref[kind]
+        src = open(os.path.join(root, "deep-neuroevolution_b200", "es_distributed", kind + ".py")).read()
+        passed = set()
+        for node in ast.walk(ast.parse(src)):                  # keyword names of the `stats = dict(...)` call of the master
+            if isinstance(node, ast.Assign) and getattr(node.targets[0], "id", None) == "stats" and isinstance(node.value, ast.Call) \
+                    and getattr(node.value.func, "id", None) == "dict":
+                passed |= {k.arg for k in node.value.keywords}
+        need = [k for k in ref[kind] if k not in ES._ROW_DEFAULTS and k != "UniqueWorkers"]
+        assert set(need) <= passed, (kind, sorted(set(need) - passed))
+        assert 'reference_row("%s", stats, world)' % kind in src
+        row = ES.reference_row(kind, dict({k: 1.0 for k in need}, Extra=5, NoveltyMean=2.0), world=3)
+        assert list(row)[:len(ref[kind])] == ref[kind] and list(row)[len(ref[kind]):] == ["Extra", "NoveltyMean"]
+        assert row["UniqueWorkers"] == 3 and row["EvalEpCount"] == 0 and np.isnan(row["EvalEpRewMean"])
+    # ES: the master builds its row key by key in the reference's order
+    es_src = open(os.path.join(root, "deep-neuroevolution_b200", "es_distributed", "es.py")).read()
+    call = next(n for n in ast.walk(ast.parse(es_src)) if isinstance(n, ast.Call) and getattr(n.func, "id", None) == "GenerationStats")
+    assert [k.arg for k in call.keywords] == ref["es"]
